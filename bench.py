@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the LstmProjectedStreams BPTT hot path (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one BPTT chunk of synthetic input: for every stacked
+layer Propagate, then Backpropagate from a synthetic out_diff at the top, the gradient all-reduce
+(N > 1), and Update -- what nnet.Propagate / nnet.Backpropagate do per chunk in
+google/nnetbin/bd-nnet-train-lstm-streams.cc:209-229.  A frame is one (stream, timestep) row;
+value = N * S * T * steps / seconds, the whole-job aggregate (weak scaling: S per GPU fixed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the shape north_star's target is quoted on (NumStream=64, 800/512)
+    "cfg3": dict(layers=[(40, 800, 512), (512, 800, 512)], S=64, T=20,
+                 desc="configs[2]: stacked 2x LstmProjectedStreams (40->800/512->800/512), NumStream=64 per GPU, "
+                      "20-frame BPTT, fwd+bwd+update"),
+    "cfg3-layer1": dict(layers=[(40, 800, 512)], S=64, T=20,
+                        desc="configs[2] first layer only: LstmProjectedStreams 40->800/512, NumStream=64, T=20"),
+    "cfg2": dict(layers=[(40, 800, 512)], S=4, T=20,
+                 desc="configs[1]: LstmProjectedStreams 40->800/512, NumStream=4, 20-frame BPTT (recipe default)"),
+    "cfg4-lstm": dict(layers=[(40, 800, 512)], S=32, T=20,
+                      desc="configs[3] LSTM part: 40->800/512, NumStream=32 per GPU (256 over 8), T=20"),
+}
+LR, MOMENTUM, PARAM_SCALE = 1e-5, 0.9, 0.01  # google/train_lstm_streams.sh:3-8, google/nnet.proto:3
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+        self.load = False
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append((self.load, parts))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        rows = [p for load, p in self.rows if load] or [p for _, p in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(p[0]) for p in rows if p[0].replace(".", "").isdigit())
+        mx = [float(p[1]) for p in rows if p[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(p[3 + k].lower().startswith("active") for p in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic bytes / flops (DESIGN.md "Kernels")
+# ---------------------------------------------------------------------------------------------
+def alg_fwd_kernel(I, C, R, S, T):
+    ts = S * T
+    rd = ts * 4 * C + (4 * C * R + R * C) + S * (C + R)          # pre-activations, weights once, carried state
+    wr = ts * 4 * C + 3 * ts * C + 2 * ts * R + S * (C + R)      # g,i,f,o | c,h,m | r (record + out) | state
+    flops = ts * (2 * R * 4 * C + 2 * C * R)
+    return 4 * (rd + wr), flops
+
+
+def alg_bwd_kernel(I, C, R, S, T):
+    ts = S * T
+    rd = ts * 4 * C + (T + 1) * S * C + ts * C + ts * R + (4 * C * R + R * C)  # g,i,f,o | c | h | out_diff | weights
+    wr = ts * 4 * C + ts * R + 7 * C                                           # DGIFO | DR | bias+peephole grads
+    flops = ts * (2 * R * 4 * C + 2 * C * R)
+    return 4 * (rd + wr), flops
+
+
+def alg_chunk(I, C, R, S, T):
+    """F = S*T*(6*I*4C + 6*R*4C + 6*C*R); compulsory bytes B."""
+    P = 4 * C * I + 4 * C * R + 7 * C + R * C
+    F = S * T * (6 * I * 4 * C + 6 * R * 4 * C + 6 * C * R)
+    B = S * T * (4 * I + 4 * (7 * C + R) + 4 * R) + S * T * (4 * R + 8 * (7 * C + R) + 4 * I) + 4 * P * 4
+    return B, F
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle (restatement of the reference's CPU matrix path,
+# cblas sgemm + serial elementwise loops) on this box's host cores
+# ---------------------------------------------------------------------------------------------
+class CpuStack:
+    def __init__(self, wl, threads=None):
+        from oracle import oracle_py
+        oracle_py.build()
+        self.threads = oracle_py.use_openblas(threads) or 1
+        self.blas = "openblas(scipy-bundled)" if self.threads and oracle_py._blas_keepalive else "builtin-loops"
+        self.S, self.T = wl["S"], wl["T"]
+        self.layers = []
+        for li, (I, C, R) in enumerate(wl["layers"]):
+            o = oracle_py.Oracle(I, C, R, self.S, np.float32)
+            o.set_params(oracle_py.init_params(I, C, R, PARAM_SCALE, 4321 + li))
+            self.layers.append(o)
+        rng = np.random.RandomState(1234)
+        I0, Rtop = wl["layers"][0][0], wl["layers"][-1][2]
+        self.x = rng.randn(self.S * self.T, I0).astype(np.float32)
+        self.od = (rng.randn(self.S * self.T, Rtop) * 0.1).astype(np.float32)
+
+    def step(self):
+        acts = [self.x]
+        for o in self.layers:
+            acts.append(o.propagate(acts[-1]))
+        d = self.od
+        for li in reversed(range(len(self.layers))):
+            d = self.layers[li].backpropagate(acts[li], d, MOMENTUM, want_in_diff=True)
+        for o in self.layers:
+            o.update(LR)
+
+    def frames(self):
+        return self.S * self.T
+
+
+def run_reference_arm(args, wl):
+    stack = CpuStack(wl)
+    for _ in range(args.warmup):
+        stack.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        stack.step()
+    dt = time.perf_counter() - t0
+    val = stack.frames() * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "frames/sec LstmProjectedStreams 800-cell/512-proj BPTT", "value": val,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload, "num_stream": wl["S"], "bptt_frames": wl["T"]},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": stack.threads, "kind": "port",
+                         "sample": "%d full chunks of the workload; sgemm=%s, elementwise loops serial as in "
+                                   "kaldi-matrix.cc" % (args.steps, stack.blas)},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference cannot be compiled here (no Kaldi tree); this is the oracle restatement of its CPU "
+                "matrix path (oracle/lstmp_streams_oracle.c) on %d host threads (host has %d)" % (stack.threads,
+                                                                                                     os.cpu_count()),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference_arm(args, wl)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    import kaldi_lstm_b200 as klb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no GPU visible; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    S, T = wl["S"], wl["T"]
+    rows = S * T
+
+    # ---- model: random-init weights of the named architecture (no checkpoints offline) ----------
+    layers = []
+    for li, (I, C, R) in enumerate(wl["layers"]):
+        comp = klb.LstmProjectedStreams(I, R, device=local_rank, max_frames=T)
+        comp.InitData("<CellDim> %d <NumStream> %d <ParamScale> %g" % (C, S, PARAM_SCALE), seed=4321 + li)
+        comp.SetTrainOptions(klb.NnetTrainOptions(LR, MOMENTUM))
+        layers.append(comp)
+    grad_views = [c.engine.arena_tensor(2) for c in layers]
+    I0, Rtop = wl["layers"][0][0], wl["layers"][-1][2]
+
+    # ---- synthetic data: ring of distinct chunks whose total size exceeds the 126 MB L2 ---------
+    bytes_per_chunk = rows * (I0 + Rtop) * 4
+    ring = max(4, int(160e6 // bytes_per_chunk) + 1)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    X = torch.randn(ring, rows, I0, device=dev, generator=g)                  # "40-dim fbank" after CMVN ~ N(0,1)
+    OD = torch.randn(ring, rows, Rtop, device=dev, generator=g) * 0.1         # synthetic loss gradient
+    outs = [torch.empty(rows, R, device=dev) for (_, _, R) in wl["layers"]]
+    in_diffs = [None] + [torch.empty(rows, I, device=dev) for (I, _, _) in wl["layers"][1:]]
+
+    def compute(x, od, i):
+        # staggered synthetic utterance boundaries: stream s starts a new utterance every 50 chunks
+        flags = [1 if (i + s) % 50 == 0 else 0 for s in range(S)]
+        h = x
+        for li, comp in enumerate(layers):
+            comp.Reset(flags)                                 # nnet.Reset(new_utt_flags), TRAIN.cc:209
+            comp.PropagateFnc(h, outs[li])                    # nnet.Propagate, TRAIN.cc:215
+            h = outs[li]
+        d = od
+        for li in reversed(range(len(layers))):               # nnet.Backpropagate, TRAIN.cc:228
+            inp = x if li == 0 else outs[li - 1]
+            layers[li].BackpropagateFnc(inp, outs[li], d, in_diffs[li])
+            d = in_diffs[li]
+        if world > 1:                                         # one sum all-reduce of the fresh gradients per Update
+            for gv in grad_views:
+                dist.all_reduce(gv, op=dist.ReduceOp.SUM)
+        for comp in layers:
+            comp.Update()
+
+    def launches():
+        return sum(c.engine.info()["kernel_launches"] for c in layers)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- warm-up, then the timed region (device-resident inputs) ---------------------------------
+    for i in range(max(3, args.warmup)):
+        compute(X[i % ring], OD[i % ring], i)
+    sync_all()
+    sampler.load = True
+    l0 = launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        compute(X[i % ring], OD[i % ring], i)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = launches() - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * rows * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end: host buffers in, host scalar out, through the same public calls --------------
+    e2e = None
+    if not args.no_e2e:
+        nh = min(ring, 16)
+        Xh = [torch.randn(rows, I0).pin_memory() for _ in range(nh)]
+        ODh = [(torch.randn(rows, Rtop) * 0.1).pin_memory() for _ in range(nh)]
+        xd, odd = torch.empty(rows, I0, device=dev), torch.empty(rows, Rtop, device=dev)
+        res = torch.empty(1).pin_memory()
+
+        def e2e_step(i):
+            xd.copy_(Xh[i % nh], non_blocking=True)          # feature chunk H2D (TRAIN.cc:212 CuMatrix(feat))
+            odd.copy_(ODh[i % nh], non_blocking=True)        # loss gradient stand-in (targets go H2D in LOSS.cc:96)
+            compute(xd, odd, i)
+            res.copy_(outs[-1][rows - S:].sum().reshape(1), non_blocking=False)   # progress metric D2H + sync
+            return float(res[0])
+
+        for i in range(3):
+            e2e_step(i)
+        sync_all()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        s1.record()
+        sync_all()
+        ems = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": world * rows * args.steps / (ems * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": rows * (I0 + Rtop) * 4, "d2h_bytes_per_step": 4,
+               "ms_per_step": ems / args.steps,
+               "what": "pinned host feature chunk + loss-gradient chunk H2D, Reset/Propagate/Backpropagate/"
+                       "[allreduce]/Update through the component API, 4-byte output checksum D2H with sync, "
+                       "every step"}
+
+    # ---- per-kernel device times (engine-side CUDA events on the launch stream) -------------------
+    for c in layers:
+        c.engine.timing_enable(True)
+    nprof = min(args.steps, 50)
+    for i in range(nprof):
+        compute(X[i % ring], OD[i % ring], i)
+    kinds = {}
+    for c in layers:
+        for k, (tms, cnt) in c.engine.timing_read().items():
+            a = kinds.setdefault(k, [0.0, 0])
+            a[0] += tms
+            a[1] += cnt
+        c.engine.timing_enable(False)
+    sampler.load = False
+    sync_all()
+    tot = sum(v[0] for v in kinds.values()) or 1.0
+    kernels = {k: {"us_per_launch": 1e3 * v[0] / max(v[1], 1), "launches_per_step": v[1] / nprof,
+                   "share": v[0] / tot} for k, v in kinds.items() if v[1]}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    dom = max(("fwd_recurrent", "bwd_recurrent"), key=lambda k: kinds.get(k, [0, 0])[0])
+    I_, C_, R_ = wl["layers"][0]
+    ab, af = (alg_bwd_kernel if dom == "bwd_recurrent" else alg_fwd_kernel)(I_, C_, R_, S, T)
+    dom_us = kernels.get(dom, {}).get("us_per_launch", float("nan"))
+    ach = ab / (dom_us * 1e-6) / 1e9 if dom_us == dom_us else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = {"kernel": "lstmp_%s_kernel" % dom.split("_")[0], "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None, "traffic": traffic,
+                "peak_source": peak_src, "alg_bytes_per_launch": ab, "alg_flops_per_launch": af,
+                "us_per_launch": dom_us, "achieved_tflops_fp32": af / (dom_us * 1e-6) / 1e12 if ach else None}
+    cb, cf = 0, 0
+    for (I, C, R) in wl["layers"]:
+        b_, f_ = alg_chunk(I, C, R, S, T)
+        cb, cf = cb + b_, cf + f_
+    step_us = 1e3 * ms / args.steps
+    chunk_roofline = {"alg_bytes_per_step": cb, "alg_flops_per_step": cf,
+                      "hbm_bound_us": cb / (hbm_peak * 1e9) * 1e6,
+                      "frac_of_hbm_bound": (cb / (hbm_peak * 1e9) * 1e6) / step_us}
+
+    if rank == 0:
+        sampler.stop()
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        stack = CpuStack(wl)
+        stack.step()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 2 or (time.perf_counter() - t0 < args.cpu_seconds and n < 200):
+            stack.step()
+            n += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": stack.frames() * n / dt, "unit": "frames/s", "cores": stack.threads, "kind": "port",
+                        "sample": "%d full chunks (%.1f s) of the same workload; sgemm=%s on %d threads (host has %d "
+                                  "cpus), elementwise loops serial as in kaldi-matrix.cc" % (
+                                      n, dt, stack.blas, stack.threads, os.cpu_count())}
+
+    if rank == 0:
+        info = layers[0].engine.info()
+        line = {
+            "metric": "frames/sec LstmProjectedStreams 800-cell/512-proj BPTT", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload, "num_stream_per_gpu": S, "bptt_frames": T,
+                       "learn_rate": LR, "momentum": MOMENTUM, "param_scale": PARAM_SCALE,
+                       "parallelism": "streams sharded over %d GPU(s), 1 NCCL sum-allreduce of the gradients per "
+                                      "Update" % world if world > 1 else "1 GPU",
+                       "l2": "inputs larger than L2: ring of %d distinct (feature, out_diff) chunks = %.0f MB" % (
+                           ring, ring * bytes_per_chunk / 1e6),
+                       "decomposition": {k: info[k] for k in ("ngroups", "ctas_per_group", "streams_per_group",
+                                                              "cells_per_cta", "rcols_per_cta", "gemm_backend")}},
+            "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": sampler.summary(), "roofline": roofline,
+            "chunk_roofline": chunk_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

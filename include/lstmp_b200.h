@@ -1,0 +1,157 @@
+/*
+ * lstmp_b200.h -- C ABI of the B200-native LstmProjectedStreams engine (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of dophist/kaldi-lstm: the multi-stream
+ * projected LSTM layer's forward / truncated-BPTT backward / SGD update.  Each entry
+ * point replaces what the reference's component does through CuMatrix calls
+ * (citations are relative to the reference tree, google/nnet/bd-nnet-lstm-projected-streams.h
+ * = "LPS.h"):
+ *
+ *   lstmp_b200_create              ctor + InitData/ReadData buffer allocation   LPS.h:27-33,76-97,119-130
+ *   lstmp_b200_set_params/get_...  ReadData / WriteData / GetParams            LPS.h:101-189
+ *   lstmp_b200_reset               Reset(std::vector<int>&)                    LPS.h:212-220
+ *   lstmp_b200_propagate           PropagateFnc(in, out)                       LPS.h:222-332
+ *   lstmp_b200_backpropagate       BackpropagateFnc(in, out, out_diff, in_diff) LPS.h:334-499
+ *   lstmp_b200_update              momentum accumulation + Update()            LPS.h:465-487,501-512
+ *
+ * The kernels fused behind these calls also replace google/cudamatrix/bd-cu-kernels.cu
+ * (cudaF_add_mat_diag_vec / cudaF_add_mat_dot_mat, bd-cu-kernels-ansi.h:9-22) and the
+ * CuMatrixBase methods listed in SURVEY.md section 8a (a6-a10).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success, a negative
+ *     LSTMP_B200_E* code on a usage error, or a positive cudaError_t value on a CUDA
+ *     failure.  lstmp_b200_last_error() gives a message for the calling thread.
+ *   - matrices are row-major fp32 with a leading dimension (row stride) in floats,
+ *     exactly Kaldi's CuMatrixBase {data_, num_cols_, num_rows_, stride_} layout
+ *     (google/cudamatrix/cu-matrix.h:479-489).  `in`, `out`, `out_diff`, `in_diff` are
+ *     DEVICE pointers owned by the caller (Nnet's propagate/backpropagate buffers).
+ *   - frame rows are time-major: row = t*S + s (bd-nnet-train-lstm-streams.cc:187-206).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is
+ *     what Kaldi's CuDevice uses).
+ *   - there is NO CPU fallback: every entry point needs a CUDA device of compute
+ *     capability 10.x and fails loudly otherwise.
+ */
+#ifndef LSTMP_B200_H_
+#define LSTMP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lstmp_b200_engine* lstmp_b200_handle_t;
+
+enum {
+  LSTMP_B200_OK = 0,
+  LSTMP_B200_EINVAL = -1,      /* bad argument / shape (KALDI_ASSERT in the reference) */
+  LSTMP_B200_ENODEV = -2,      /* no sm_100 device */
+  LSTMP_B200_ENOMEM = -3,      /* shape does not fit on-chip / device memory */
+  LSTMP_B200_ESTATE = -4,      /* call order violated (e.g. backpropagate without propagate) */
+  LSTMP_B200_EUNSUPPORTED = -5 /* NCCL entry point without NCCL at run time, etc. */
+};
+
+/* ABI version of this header (bumped on incompatible change). */
+int lstmp_b200_abi_version(void);
+const char* lstmp_b200_last_error(void);
+
+/* input_dim I, cell_dim C (<CellDim>), recur_dim R (= OutputDim, LPS.h:30), num_stream S
+ * (<NumStream>), max_frames = largest T (BPTT chunk length) a later call will use.
+ * Requires I % 4 == 0, C % 4 == 0, R % 4 == 0 (128-bit vector / TMA bulk granularity).
+ * Parameters start at zero; gradient/momentum buffers and the carried state start at zero
+ * (LPS.h:76,89-97). */
+int lstmp_b200_create(int input_dim, int cell_dim, int recur_dim, int num_stream, int max_frames, int device,
+                      lstmp_b200_handle_t* out);
+int lstmp_b200_destroy(lstmp_b200_handle_t h);
+/* Deep copy: parameters, momentum buffers and carried state (Component::Copy, LPS.h:38). */
+int lstmp_b200_clone(lstmp_b200_handle_t src, lstmp_b200_handle_t* out);
+
+/* NumParams() (LPS.h:152-160). */
+int lstmp_b200_num_params(lstmp_b200_handle_t h, size_t* n);
+
+/* Parameters as the seven tensors of LPS.h:590-613.  Pointers may be host or device
+ * (cudaMemcpyDefault); ld* are row strides in floats.
+ *   w_gifo_x [4C x I], w_gifo_r [4C x R], bias [4C], peephole_{i,f,o}_c [C], w_r_m [R x C]
+ * Gate order along 4C is g,i,f,o (LPS.h:234-243). */
+int lstmp_b200_set_params(lstmp_b200_handle_t h, const float* w_gifo_x, size_t ld_x, const float* w_gifo_r,
+                          size_t ld_r, const float* bias, const float* peephole_i_c, const float* peephole_f_c,
+                          const float* peephole_o_c, const float* w_r_m, size_t ld_m, void* stream);
+int lstmp_b200_get_params(lstmp_b200_handle_t h, float* w_gifo_x, size_t ld_x, float* w_gifo_r, size_t ld_r,
+                          float* bias, float* peephole_i_c, float* peephole_f_c, float* peephole_o_c,
+                          float* w_r_m, size_t ld_m, void* stream);
+/* Flat vector in GetParams() order (LPS.h:162-189); host or device pointer.
+ * which: 0 = parameters, 1 = momentum-accumulated gradients (*_corr_), 2 = fresh gradient of the
+ * last backpropagate (before momentum / all-reduce). */
+int lstmp_b200_get_flat(lstmp_b200_handle_t h, int which, float* dst, void* stream);
+int lstmp_b200_set_flat(lstmp_b200_handle_t h, int which, const float* src, void* stream);
+/* Device address + length of the same three arenas, e.g. to all-reduce the fresh gradient with the
+ * caller's own communicator between backpropagate and update. */
+int lstmp_b200_arena(lstmp_b200_handle_t h, int which, float** dev_ptr, size_t* count);
+
+/* Carried state prev_nnet_state_ (LPS.h:583): only the c and r column blocks are ever read
+ * (LPS.h:275-281), so only those are exposed.  c [S x C], r [S x R]; host or device pointers. */
+int lstmp_b200_get_state(lstmp_b200_handle_t h, float* c, size_t ld_c, float* r, size_t ld_r, void* stream);
+int lstmp_b200_set_state(lstmp_b200_handle_t h, const float* c, size_t ld_c, const float* r, size_t ld_r,
+                         void* stream);
+
+/* Reset (LPS.h:212-220): host_flags[s] == 1 zeroes stream s's carried state.  n must equal S. */
+int lstmp_b200_reset(lstmp_b200_handle_t h, const int32_t* host_flags, int n, void* stream);
+
+/* PropagateFnc (LPS.h:222-332).  in [num_rows x I], out [num_rows x R]; num_rows = T*S with
+ * T <= max_frames, else LSTMP_B200_EINVAL (the reference asserts, LPS.h:225). */
+int lstmp_b200_propagate(lstmp_b200_handle_t h, const float* in, size_t ld_in, float* out, size_t ld_out,
+                         int num_rows, void* stream);
+
+/* BackpropagateFnc (LPS.h:334-499) for the chunk of the last propagate.  in_diff may be NULL
+ * (first trainable layer).  Leaves the fresh gradient (sum over all T*S rows, LPS.h:468-487
+ * with beta = 0) in arena 2; momentum is applied in lstmp_b200_update so that a data-parallel
+ * caller can all-reduce the fresh gradient first. */
+int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, size_t ld_in, const float* out_diff,
+                             size_t ld_od, float* in_diff, size_t ld_id, int num_rows, void* stream);
+
+/* corr = G + momentum*corr (LPS.h:465-487), then param -= learn_rate*corr (LPS.h:501-512). */
+int lstmp_b200_update(lstmp_b200_handle_t h, float learn_rate, float momentum, void* stream);
+
+/* Sum the fresh gradient arena over all ranks of `nccl_comm` (an ncclComm_t) in place, on
+ * `stream`.  NCCL is resolved at run time with dlopen("libnccl.so.2"); returns
+ * LSTMP_B200_EUNSUPPORTED when it cannot be loaded. */
+int lstmp_b200_allreduce_grads_nccl(lstmp_b200_handle_t h, void* nccl_comm, void* stream);
+
+/* Introspection for benchmarks and tests. */
+typedef struct {
+  int input_dim, cell_dim, recur_dim, num_stream, max_frames;
+  int sm_count;
+  int ngroups, ctas_per_group, streams_per_group, cells_per_cta, rcols_per_cta;
+  size_t fwd_smem_bytes, bwd_smem_bytes;
+  size_t workspace_bytes;          /* activations + scratch owned by the engine */
+  unsigned long long kernel_launches; /* kernels launched by this handle so far */
+  int gemm_backend;                /* 0 = fp32 SIMT, 1 = tcgen05 3xTF32 */
+} lstmp_b200_info_t;
+int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* info);
+
+/* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel this
+ * handle launches while enabled).  kinds: 0 input GEMM (+bias), 1 forward recurrent kernel,
+ * 2 backward recurrent kernel, 3 in_diff GEMM, 4 weight-gradient GEMMs, 5 bias/peephole gradient
+ * gather, 6 update, 7 reset.  lstmp_b200_timing_read synchronises, returns the accumulated
+ * milliseconds / launch counts since the last read and clears them. */
+#define LSTMP_B200_TIMING_KINDS 8
+typedef struct {
+  double ms[LSTMP_B200_TIMING_KINDS];
+  unsigned long long count[LSTMP_B200_TIMING_KINDS];
+} lstmp_b200_timing_t;
+int lstmp_b200_timing_enable(lstmp_b200_handle_t h, int on);
+int lstmp_b200_timing_read(lstmp_b200_handle_t h, lstmp_b200_timing_t* out);
+
+/* Debug/test access to the per-chunk activation record in the reference's propagate_buf_ /
+ * backpropagate_buf_ column layout [g|i|f|o|c|h|m (C each)|r (R)] for frames 1..T
+ * (LPS.h:234-241,355-362).  dst is a HOST or device buffer of T*S rows x (7C+R).  In the backward
+ * record only the g,i,f,o and r blocks are materialised (d_c/d_h/d_m never leave the SM); the
+ * others are written as zeros. */
+int lstmp_b200_get_record(lstmp_b200_handle_t h, int backward, float* dst, size_t ld_dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSTMP_B200_H_ */

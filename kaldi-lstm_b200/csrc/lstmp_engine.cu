@@ -1,0 +1,605 @@
+// Host side of the C ABI (include/lstmp_b200.h): owns parameters, momentum buffers, carried
+// state and the per-chunk activation record in HBM; decides the work decomposition; launches
+// the sm_100a kernels.  No CPU compute path exists here by design.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lstmp_b200.h"
+#include "lstmp_kernels.h"
+
+using namespace lstmp;
+
+namespace lstmp {
+cudaError_t launch_gemm_simt(float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
+                             long long lda, int tA, const float* B, long long ldb, int tB, float beta,
+                             const float* bias, cudaStream_t stream);
+#ifdef LSTMP_HAVE_TC_GEMM
+cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
+                           long long lda, int tA, const float* B, long long ldb, int tB, float beta,
+                           const float* bias, cudaStream_t stream, bool* handled);
+#endif
+}  // namespace lstmp
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail((int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct lstmp_b200_engine {
+  int I = 0, C = 0, R = 0, S = 0, Tmax = 0, device = 0, sm_count = 0;
+  size_t nparams = 0;
+  // arenas, GetParams order (LPS.h:162-189)
+  float *params = nullptr, *corr = nullptr, *grads = nullptr;
+  size_t off_wx = 0, off_wr = 0, off_bias = 0, off_pi = 0, off_pf = 0, off_po = 0, off_wm = 0;
+  // carried state (c and r blocks of prev_nnet_state_, LPS.h:583)
+  float *state_c = nullptr, *state_r = nullptr;
+  // per-chunk record
+  float *gifo = nullptr, *cbuf = nullptr, *hbuf = nullptr, *mbuf = nullptr, *rbuf = nullptr;
+  float *dgifo = nullptr, *dr = nullptr, *scratch = nullptr, *small_grads = nullptr;
+  unsigned* bar = nullptr;
+  unsigned bar_base[kMaxGroupsHost] = {0};
+  size_t workspace_bytes = 0;
+  Decomp d{};
+  FwdParams fp{};
+  BwdParams bp{};
+  size_t fwd_smem = 0, bwd_smem = 0;
+  int T_last = 0;        // frames of the last propagate (0 = none)
+  bool have_bwd = false; // a backpropagate record exists for T_last
+  unsigned long long launches = 0;
+  int gemm_backend = 0;
+  // optional per-kernel event timing
+  bool timing = false;
+  struct Ev { int kind; cudaEvent_t a, b; };
+  std::vector<Ev> events;
+};
+
+// RAII: brackets one kernel launch with events on its stream when timing is enabled.
+struct Timed {
+  lstmp_b200_engine* h;
+  int kind;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Timed(lstmp_b200_engine* h_, int kind_, cudaStream_t st_) : h(h_), kind(kind_), st(st_) {
+    if (h->timing && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+  }
+  ~Timed() {
+    if (a && b) {
+      cudaEventRecord(b, st);
+      h->events.push_back({kind, a, b});
+    }
+  }
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+static bool make_decomp(int C, int R, int S, int sm_count, size_t smem_limit, int ngroups, Decomp* out,
+                        FwdParams* fp, BwdParams* bp, size_t* fs, size_t* bs) {
+  if (ngroups < 1 || ngroups > kMaxGroupsHost || S % ngroups != 0) return false;
+  Decomp d;
+  d.ngroups = ngroups;
+  d.ctas_per_group = sm_count / ngroups;
+  if (d.ctas_per_group < 1) return false;
+  d.Sg = S / ngroups;
+  d.cpc = (C + d.ctas_per_group - 1) / d.ctas_per_group;
+  d.rpc = (R + d.ctas_per_group - 1) / d.ctas_per_group;
+  long long per = (long long)d.Sg * R;
+  long long piece = (per + d.ctas_per_group - 1) / d.ctas_per_group;
+  d.piece = (int)((piece + 3) & ~3LL);
+  d.KC = d.Sg <= 16 ? 128 : 64;
+  FwdParams f{};
+  BwdParams b{};
+  size_t fsz = fwd_smem_floats(C, R, d, &f) * sizeof(float);
+  size_t bsz = bwd_smem_floats(C, R, d, &b) * sizeof(float);
+  if (fsz > smem_limit || bsz > smem_limit) return false;
+  *out = d;
+  *fp = f;
+  *bp = b;
+  *fs = fsz;
+  *bs = bsz;
+  return true;
+}
+
+extern "C" int lstmp_b200_abi_version(void) { return 1; }
+extern "C" const char* lstmp_b200_last_error(void) { return g_err.c_str(); }
+
+static int alloc_f(float** p, size_t n, size_t* total) {
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(float));
+  if (e != cudaSuccess) return fail(LSTMP_B200_ENOMEM, "cudaMalloc(%zu floats): %s", n, cudaGetErrorString(e));
+  e = cudaMemset(*p, 0, n * sizeof(float));
+  if (e != cudaSuccess) return fail((int)e, "cudaMemset: %s", cudaGetErrorString(e));
+  *total += n * sizeof(float);
+  return 0;
+}
+
+extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  float* bufs[] = {h->params, h->corr, h->grads, h->state_c, h->state_r, h->gifo, h->cbuf, h->hbuf,
+                   h->mbuf,   h->rbuf, h->dgifo, h->dr,      h->scratch, h->small_grads};
+  for (float* b : bufs)
+    if (b) cudaFree(b);
+  if (h->bar) cudaFree(h->bar);
+  delete h;
+  return 0;
+}
+
+extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int device, lstmp_b200_handle_t* out) {
+  if (!out) return fail(LSTMP_B200_EINVAL, "out handle is NULL");
+  *out = nullptr;
+  if (I <= 0 || C <= 0 || R <= 0 || S <= 0 || Tmax <= 0)
+    return fail(LSTMP_B200_EINVAL, "dimensions must be positive (I=%d C=%d R=%d S=%d T=%d)", I, C, R, S, Tmax);
+  if (I % 4 || C % 4 || R % 4)
+    return fail(LSTMP_B200_EINVAL, "input_dim, cell_dim and recur_dim must be multiples of 4 (I=%d C=%d R=%d)", I, C, R);
+  if (S > 1024) return fail(LSTMP_B200_EINVAL, "num_stream %d > 1024 not supported", S);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LSTMP_B200_ENODEV, "no CUDA device: %s (this engine has no CPU path)", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(LSTMP_B200_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(LSTMP_B200_ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                prop.minor);
+  int coop = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (!coop) return fail(LSTMP_B200_ENODEV, "device %d lacks cooperative launch", device);
+
+  lstmp_b200_engine* h = new (std::nothrow) lstmp_b200_engine();
+  if (!h) return fail(LSTMP_B200_ENOMEM, "host allocation failed");
+  h->I = I; h->C = C; h->R = R; h->S = S; h->Tmax = Tmax; h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  int sm_use = env_int("LSTMP_B200_MAX_CTAS", h->sm_count);
+  if (sm_use < 1 || sm_use > h->sm_count) sm_use = h->sm_count;
+  size_t smem_limit = prop.sharedMemPerBlockOptin;
+
+  // work decomposition: most stream groups (least all-gather traffic per SM) whose weight
+  // slices still fit in shared memory, keeping >= 16 streams per group.
+  int forced = env_int("LSTMP_B200_NGROUPS", 0);
+  bool ok = false;
+  if (forced > 0) {
+    ok = make_decomp(C, R, S, sm_use, smem_limit, forced, &h->d, &h->fp, &h->bp, &h->fwd_smem, &h->bwd_smem);
+    if (!ok) {
+      delete h;
+      return fail(LSTMP_B200_ENOMEM, "LSTMP_B200_NGROUPS=%d does not fit (S=%d, smem limit %zu)", forced, S, smem_limit);
+    }
+  } else {
+    for (int g = 8; g >= 1 && !ok; g >>= 1) {
+      if (S % g != 0 || (g > 1 && S / g < 16)) continue;
+      ok = make_decomp(C, R, S, sm_use, smem_limit, g, &h->d, &h->fp, &h->bp, &h->fwd_smem, &h->bwd_smem);
+    }
+  }
+  if (!ok) {
+    delete h;
+    return fail(LSTMP_B200_ENOMEM,
+                "weight slices of a %d-cell/%d-proj layer do not fit in %zu B of shared memory per SM over %d SMs "
+                "(weights-streamed mode not built yet)",
+                C, R, smem_limit, sm_use);
+  }
+  e = set_kernel_smem_limits(h->fwd_smem, h->bwd_smem);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail((int)e, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e));
+  }
+
+  // arenas
+  size_t off = 0;
+  h->off_wx = off; off += (size_t)4 * C * I;
+  h->off_wr = off; off += (size_t)4 * C * R;
+  h->off_bias = off; off += (size_t)4 * C;
+  h->off_pi = off; off += C;
+  h->off_pf = off; off += C;
+  h->off_po = off; off += C;
+  h->off_wm = off; off += (size_t)R * C;
+  h->nparams = off;
+  size_t ws = 0, dummy = 0;
+  const size_t TS = (size_t)Tmax * S, TS1 = (size_t)(Tmax + 1) * S;
+  int rc = 0;
+  if ((rc = alloc_f(&h->params, h->nparams, &dummy)) || (rc = alloc_f(&h->corr, h->nparams, &dummy)) ||
+      (rc = alloc_f(&h->grads, h->nparams, &dummy)) || (rc = alloc_f(&h->state_c, (size_t)S * C, &dummy)) ||
+      (rc = alloc_f(&h->state_r, (size_t)S * R, &dummy)) || (rc = alloc_f(&h->gifo, TS * 4 * C, &ws)) ||
+      (rc = alloc_f(&h->cbuf, TS1 * C, &ws)) || (rc = alloc_f(&h->hbuf, TS * C, &ws)) ||
+      (rc = alloc_f(&h->mbuf, TS * C, &ws)) || (rc = alloc_f(&h->rbuf, TS1 * R, &ws)) ||
+      (rc = alloc_f(&h->dgifo, TS * 4 * C, &ws)) || (rc = alloc_f(&h->dr, TS * R, &ws)) ||
+      (rc = alloc_f(&h->scratch, (size_t)h->d.ngroups * h->d.ctas_per_group * h->d.Sg * R, &ws)) ||
+      (rc = alloc_f(&h->small_grads, (size_t)h->d.ngroups * 7 * C, &ws))) {
+    lstmp_b200_destroy(h);
+    return rc;
+  }
+  e = cudaMalloc((void**)&h->bar, kMaxGroupsHost * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(h->bar, 0, kMaxGroupsHost * sizeof(unsigned));
+  if (e != cudaSuccess) {
+    lstmp_b200_destroy(h);
+    return fail((int)e, "barrier counters: %s", cudaGetErrorString(e));
+  }
+  h->workspace_bytes = ws;
+  h->gemm_backend = 0;
+#ifdef LSTMP_HAVE_TC_GEMM
+  h->gemm_backend = env_int("LSTMP_B200_GEMM", 1) ? 1 : 0;
+#endif
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+
+#define CHECK_H(h)                                               \
+  do {                                                           \
+    if (!(h)) return fail(LSTMP_B200_EINVAL, "NULL handle");     \
+    CUDA_TRY(cudaSetDevice((h)->device));                        \
+  } while (0)
+
+extern "C" int lstmp_b200_num_params(lstmp_b200_handle_t h, size_t* n) {
+  if (!h || !n) return fail(LSTMP_B200_EINVAL, "NULL argument");
+  *n = h->nparams;
+  return 0;
+}
+
+static int copy2d(float* dst, size_t ldd, const float* src, size_t lds, size_t cols, size_t rows, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return 0;
+  CUDA_TRY(cudaMemcpy2DAsync(dst, ldd * sizeof(float), src, lds * sizeof(float), cols * sizeof(float), rows,
+                             cudaMemcpyDefault, st));
+  return 0;
+}
+
+extern "C" int lstmp_b200_set_params(lstmp_b200_handle_t h, const float* wx, size_t ld_x, const float* wr,
+                                     size_t ld_r, const float* bias, const float* pi, const float* pf,
+                                     const float* po, const float* wm, size_t ld_m, void* stream) {
+  CHECK_H(h);
+  if (!wx || !wr || !bias || !pi || !pf || !po || !wm) return fail(LSTMP_B200_EINVAL, "NULL parameter pointer");
+  if (ld_x < (size_t)h->I || ld_r < (size_t)h->R || ld_m < (size_t)h->C) return fail(LSTMP_B200_EINVAL, "stride < columns");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  float* P = h->params;
+  if ((rc = copy2d(P + h->off_wx, h->I, wx, ld_x, h->I, (size_t)4 * h->C, st))) return rc;
+  if ((rc = copy2d(P + h->off_wr, h->R, wr, ld_r, h->R, (size_t)4 * h->C, st))) return rc;
+  if ((rc = copy2d(P + h->off_bias, 4 * h->C, bias, 4 * h->C, (size_t)4 * h->C, 1, st))) return rc;
+  if ((rc = copy2d(P + h->off_pi, h->C, pi, h->C, h->C, 1, st))) return rc;
+  if ((rc = copy2d(P + h->off_pf, h->C, pf, h->C, h->C, 1, st))) return rc;
+  if ((rc = copy2d(P + h->off_po, h->C, po, h->C, h->C, 1, st))) return rc;
+  if ((rc = copy2d(P + h->off_wm, h->C, wm, ld_m, h->C, h->R, st))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int lstmp_b200_get_params(lstmp_b200_handle_t h, float* wx, size_t ld_x, float* wr, size_t ld_r,
+                                     float* bias, float* pi, float* pf, float* po, float* wm, size_t ld_m,
+                                     void* stream) {
+  CHECK_H(h);
+  if (!wx || !wr || !bias || !pi || !pf || !po || !wm) return fail(LSTMP_B200_EINVAL, "NULL parameter pointer");
+  if (ld_x < (size_t)h->I || ld_r < (size_t)h->R || ld_m < (size_t)h->C) return fail(LSTMP_B200_EINVAL, "stride < columns");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  const float* P = h->params;
+  if ((rc = copy2d(wx, ld_x, P + h->off_wx, h->I, h->I, (size_t)4 * h->C, st))) return rc;
+  if ((rc = copy2d(wr, ld_r, P + h->off_wr, h->R, h->R, (size_t)4 * h->C, st))) return rc;
+  if ((rc = copy2d(bias, 4 * h->C, P + h->off_bias, 4 * h->C, (size_t)4 * h->C, 1, st))) return rc;
+  if ((rc = copy2d(pi, h->C, P + h->off_pi, h->C, h->C, 1, st))) return rc;
+  if ((rc = copy2d(pf, h->C, P + h->off_pf, h->C, h->C, 1, st))) return rc;
+  if ((rc = copy2d(po, h->C, P + h->off_po, h->C, h->C, 1, st))) return rc;
+  if ((rc = copy2d(wm, ld_m, P + h->off_wm, h->C, h->C, h->R, st))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static float* arena_of(lstmp_b200_handle_t h, int which) {
+  return which == 0 ? h->params : which == 1 ? h->corr : which == 2 ? h->grads : nullptr;
+}
+
+extern "C" int lstmp_b200_get_flat(lstmp_b200_handle_t h, int which, float* dst, void* stream) {
+  CHECK_H(h);
+  float* a = arena_of(h, which);
+  if (!a || !dst) return fail(LSTMP_B200_EINVAL, "bad arena %d or NULL dst", which);
+  CUDA_TRY(cudaMemcpyAsync(dst, a, h->nparams * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+extern "C" int lstmp_b200_set_flat(lstmp_b200_handle_t h, int which, const float* src, void* stream) {
+  CHECK_H(h);
+  float* a = arena_of(h, which);
+  if (!a || !src) return fail(LSTMP_B200_EINVAL, "bad arena %d or NULL src", which);
+  CUDA_TRY(cudaMemcpyAsync(a, src, h->nparams * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+extern "C" int lstmp_b200_arena(lstmp_b200_handle_t h, int which, float** dev_ptr, size_t* count) {
+  if (!h || !dev_ptr || !count) return fail(LSTMP_B200_EINVAL, "NULL argument");
+  float* a = arena_of(h, which);
+  if (!a) return fail(LSTMP_B200_EINVAL, "bad arena %d", which);
+  *dev_ptr = a;
+  *count = h->nparams;
+  return 0;
+}
+
+extern "C" int lstmp_b200_get_state(lstmp_b200_handle_t h, float* c, size_t ld_c, float* r, size_t ld_r, void* stream) {
+  CHECK_H(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (c && (rc = copy2d(c, ld_c, h->state_c, h->C, h->C, h->S, st))) return rc;
+  if (r && (rc = copy2d(r, ld_r, h->state_r, h->R, h->R, h->S, st))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+extern "C" int lstmp_b200_set_state(lstmp_b200_handle_t h, const float* c, size_t ld_c, const float* r, size_t ld_r,
+                                    void* stream) {
+  CHECK_H(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (c && (rc = copy2d(h->state_c, h->C, c, ld_c, h->C, h->S, st))) return rc;
+  if (r && (rc = copy2d(h->state_r, h->R, r, ld_r, h->R, h->S, st))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int lstmp_b200_clone(lstmp_b200_handle_t src, lstmp_b200_handle_t* out) {
+  CHECK_H(src);
+  int rc = lstmp_b200_create(src->I, src->C, src->R, src->S, src->Tmax, src->device, out);
+  if (rc) return rc;
+  lstmp_b200_handle_t d = *out;
+  CUDA_TRY(cudaMemcpy(d->params, src->params, src->nparams * sizeof(float), cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(d->corr, src->corr, src->nparams * sizeof(float), cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(d->state_c, src->state_c, (size_t)src->S * src->C * sizeof(float), cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(d->state_r, src->state_r, (size_t)src->S * src->R * sizeof(float), cudaMemcpyDeviceToDevice));
+  return 0;
+}
+
+extern "C" int lstmp_b200_reset(lstmp_b200_handle_t h, const int32_t* flags, int n, void* stream) {
+  CHECK_H(h);
+  if (!flags) return fail(LSTMP_B200_EINVAL, "NULL flags");
+  if (n != h->S) return fail(LSTMP_B200_EINVAL, "reset: %d flags for %d streams (LPS.h:214 asserts equality)", n, h->S);
+  ResetMask m;
+  memset(&m, 0, sizeof m);
+  bool any = false;
+  for (int s = 0; s < n; ++s)
+    if (flags[s] == 1) {
+      m.w[s >> 5] |= 1u << (s & 31);
+      any = true;
+    }
+  if (!any) return 0;
+  {
+    Timed tm(h, 7, (cudaStream_t)stream);
+    CUDA_TRY(launch_reset(h->state_c, h->C, h->state_r, h->R, h->S, m, (cudaStream_t)stream));
+  }
+  h->launches++;
+  return 0;
+}
+
+static int gemm(lstmp_b200_handle_t h, int kind, float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
+                long long lda, int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
+                cudaStream_t st) {
+  Timed tm(h, kind, st);
+#ifdef LSTMP_HAVE_TC_GEMM
+  if (h->gemm_backend == 1) {
+    bool handled = false;
+    CUDA_TRY(launch_gemm_tc(C, ldc, M, N, K, alpha, A, lda, tA, B, ldb, tB, beta, bias, st, &handled));
+    if (handled) {
+      h->launches++;
+      return 0;
+    }
+  }
+#endif
+  CUDA_TRY(launch_gemm_simt(C, ldc, M, N, K, alpha, A, lda, tA, B, ldb, tB, beta, bias, st));
+  h->launches++;
+  return 0;
+}
+
+extern "C" int lstmp_b200_propagate(lstmp_b200_handle_t h, const float* in, size_t ld_in, float* out, size_t ld_out,
+                                    int num_rows, void* stream) {
+  CHECK_H(h);
+  if (!in || !out) return fail(LSTMP_B200_EINVAL, "NULL in/out");
+  if (num_rows <= 0 || num_rows % h->S != 0)
+    return fail(LSTMP_B200_EINVAL, "propagate: %d rows is not a positive multiple of NumStream=%d (LPS.h:225)", num_rows, h->S);
+  const int T = num_rows / h->S;
+  if (T > h->Tmax) return fail(LSTMP_B200_EINVAL, "propagate: T=%d exceeds max_frames=%d given at create", T, h->Tmax);
+  if (ld_in < (size_t)h->I || ld_out < (size_t)h->R) return fail(LSTMP_B200_EINVAL, "stride < columns");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = h->C, R = h->R, I = h->I, S = h->S;
+  int rc;
+  // YGIFO[1..T] = in * w_gifo_x^T + bias                                  (LPS.h:246,259)
+  if ((rc = gemm(h, 0, h->gifo, 4 * C, num_rows, 4 * C, I, 1.f, in, (long long)ld_in, 0, h->params + h->off_wx, I, 1,
+                 0.f, h->params + h->off_bias, st)))
+    return rc;
+  FwdParams p = h->fp;
+  p.I = I; p.C = C; p.R = R; p.S = S; p.T = T;
+  p.d = h->d;
+  p.w_gifo_r = h->params + h->off_wr;
+  p.w_r_m = h->params + h->off_wm;
+  p.p_i = h->params + h->off_pi;
+  p.p_f = h->params + h->off_pf;
+  p.p_o = h->params + h->off_po;
+  p.gifo = h->gifo; p.cbuf = h->cbuf; p.hbuf = h->hbuf; p.mbuf = h->mbuf; p.rbuf = h->rbuf;
+  p.out = out;
+  p.ld_out = (long long)ld_out;
+  p.state_c = h->state_c;
+  p.state_r = h->state_r;
+  p.bar = h->bar;
+  for (int g = 0; g < h->d.ngroups; ++g) p.bar_base[g] = h->bar_base[g];
+  {
+    Timed tm(h, 1, st);
+    CUDA_TRY(launch_fwd(p, h->fwd_smem, st));
+  }
+  h->launches++;
+  for (int g = 0; g < h->d.ngroups; ++g) h->bar_base[g] += (unsigned)(fwd_barriers(T) * h->d.ctas_per_group);
+  h->T_last = T;
+  h->have_bwd = false;
+  return 0;
+}
+
+extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, size_t ld_in, const float* out_diff,
+                                        size_t ld_od, float* in_diff, size_t ld_id, int num_rows, void* stream) {
+  CHECK_H(h);
+  if (!in || !out_diff) return fail(LSTMP_B200_EINVAL, "NULL in/out_diff");
+  if (h->T_last == 0) return fail(LSTMP_B200_ESTATE, "backpropagate without a preceding propagate");
+  if (num_rows != h->T_last * h->S)
+    return fail(LSTMP_B200_EINVAL, "backpropagate: %d rows but the last propagate had %d", num_rows, h->T_last * h->S);
+  if (ld_in < (size_t)h->I || ld_od < (size_t)h->R || (in_diff && ld_id < (size_t)h->I))
+    return fail(LSTMP_B200_EINVAL, "stride < columns");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = h->C, R = h->R, I = h->I, S = h->S, T = h->T_last;
+  BwdParams p = h->bp;
+  p.I = I; p.C = C; p.R = R; p.S = S; p.T = T;
+  p.d = h->d;
+  p.w_gifo_r = h->params + h->off_wr;
+  p.w_r_m = h->params + h->off_wm;
+  p.p_i = h->params + h->off_pi;
+  p.p_f = h->params + h->off_pf;
+  p.p_o = h->params + h->off_po;
+  p.gifo = h->gifo; p.cbuf = h->cbuf; p.hbuf = h->hbuf;
+  p.out_diff = out_diff;
+  p.ld_od = (long long)ld_od;
+  p.dgifo = h->dgifo; p.dr = h->dr; p.scratch = h->scratch; p.small_grads = h->small_grads;
+  p.bar = h->bar;
+  for (int g = 0; g < h->d.ngroups; ++g) p.bar_base[g] = h->bar_base[g];
+  {
+    Timed tm(h, 2, st);
+    CUDA_TRY(launch_bwd(p, h->bwd_smem, st));
+  }
+  h->launches++;
+  for (int g = 0; g < h->d.ngroups; ++g) h->bar_base[g] += (unsigned)(bwd_barriers(T) * h->d.ctas_per_group);
+  // bias / peephole gradients: sum the per-group partials                  (LPS.h:474-484)
+  {
+    Timed tm(h, 5, st);
+    CUDA_TRY(launch_small_grads(h->grads + h->off_bias, h->small_grads, h->d.ngroups, 7 * C, st));
+  }
+  h->launches++;
+  int rc;
+  // in_diff = DGIFO[1..T] * w_gifo_x                                        (LPS.h:457)
+  if (in_diff && (rc = gemm(h, 3, in_diff, (long long)ld_id, num_rows, I, 4 * C, 1.f, h->dgifo, 4 * C, 0,
+                            h->params + h->off_wx, I, 0, 0.f, nullptr, st)))
+    return rc;
+  // G(w_gifo_x) = DGIFO[1..T]^T * in                                         (LPS.h:468)
+  if ((rc = gemm(h, 4, h->grads + h->off_wx, I, 4 * C, I, num_rows, 1.f, h->dgifo, 4 * C, 1, in, (long long)ld_in, 0,
+                 0.f, nullptr, st)))
+    return rc;
+  // G(w_gifo_r) = DGIFO[1..T]^T * R[0..T-1]                                  (LPS.h:471)
+  if ((rc = gemm(h, 4, h->grads + h->off_wr, R, 4 * C, R, num_rows, 1.f, h->dgifo, 4 * C, 1, h->rbuf, R, 0, 0.f,
+                 nullptr, st)))
+    return rc;
+  // G(w_r_m) = DR[1..T]^T * M[1..T]                                          (LPS.h:486)
+  if ((rc = gemm(h, 4, h->grads + h->off_wm, C, R, C, num_rows, 1.f, h->dr, R, 1, h->mbuf, C, 0, 0.f, nullptr, st)))
+    return rc;
+  h->have_bwd = true;
+  return 0;
+}
+
+extern "C" int lstmp_b200_update(lstmp_b200_handle_t h, float learn_rate, float momentum, void* stream) {
+  CHECK_H(h);
+  {
+    Timed tm(h, 6, (cudaStream_t)stream);
+    CUDA_TRY(launch_update(h->params, h->corr, h->grads, h->nparams, learn_rate, momentum, (cudaStream_t)stream));
+  }
+  h->launches++;
+  return 0;
+}
+
+// ---- NCCL, resolved at run time ------------------------------------------------------------
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+extern "C" int lstmp_b200_allreduce_grads_nccl(lstmp_b200_handle_t h, void* comm, void* stream) {
+  CHECK_H(h);
+  if (!comm) return fail(LSTMP_B200_EINVAL, "NULL ncclComm_t");
+  static nccl_allreduce_fn fn = nullptr;
+  if (!fn) {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(LSTMP_B200_EUNSUPPORTED, "dlopen(libnccl.so.2): %s", dlerror());
+    fn = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+    if (!fn) return fail(LSTMP_B200_EUNSUPPORTED, "ncclAllReduce not found");
+  }
+  // ncclFloat32 = 7, ncclSum = 0
+  int rc = fn(h->grads, h->grads, h->nparams, 7, 0, comm, (cudaStream_t)stream);
+  if (rc != 0) return fail(LSTMP_B200_EUNSUPPORTED, "ncclAllReduce returned %d", rc);
+  return 0;
+}
+
+extern "C" int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* info) {
+  if (!h || !info) return fail(LSTMP_B200_EINVAL, "NULL argument");
+  memset(info, 0, sizeof *info);
+  info->input_dim = h->I; info->cell_dim = h->C; info->recur_dim = h->R; info->num_stream = h->S;
+  info->max_frames = h->Tmax; info->sm_count = h->sm_count;
+  info->ngroups = h->d.ngroups; info->ctas_per_group = h->d.ctas_per_group; info->streams_per_group = h->d.Sg;
+  info->cells_per_cta = h->d.cpc; info->rcols_per_cta = h->d.rpc;
+  info->fwd_smem_bytes = h->fwd_smem; info->bwd_smem_bytes = h->bwd_smem;
+  info->workspace_bytes = h->workspace_bytes;
+  info->kernel_launches = h->launches;
+  info->gemm_backend = h->gemm_backend;
+  return 0;
+}
+
+extern "C" int lstmp_b200_timing_enable(lstmp_b200_handle_t h, int on) {
+  if (!h) return fail(LSTMP_B200_EINVAL, "NULL handle");
+  h->timing = on != 0;
+  return 0;
+}
+extern "C" int lstmp_b200_timing_read(lstmp_b200_handle_t h, lstmp_b200_timing_t* out) {
+  CHECK_H(h);
+  if (!out) return fail(LSTMP_B200_EINVAL, "NULL out");
+  memset(out, 0, sizeof *out);
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (auto& e : h->events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.kind >= 0 && e.kind < LSTMP_B200_TIMING_KINDS) {
+      out->ms[e.kind] += ms;
+      out->count[e.kind]++;
+    }
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  h->events.clear();
+  return 0;
+}
+
+extern "C" int lstmp_b200_get_record(lstmp_b200_handle_t h, int backward, float* dst, size_t ld, void* stream) {
+  CHECK_H(h);
+  if (!dst) return fail(LSTMP_B200_EINVAL, "NULL dst");
+  if (h->T_last == 0) return fail(LSTMP_B200_ESTATE, "no propagate record");
+  if (backward && !h->have_bwd) return fail(LSTMP_B200_ESTATE, "no backpropagate record");
+  const int C = h->C, R = h->R, S = h->S, T = h->T_last;
+  const size_t W = (size_t)7 * C + R, rows = (size_t)T * S;
+  if (ld < W) return fail(LSTMP_B200_EINVAL, "ld_dst < 7C+R");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (!backward) {
+    if ((rc = copy2d(dst, ld, h->gifo, 4 * C, 4 * C, rows, st))) return rc;
+    if ((rc = copy2d(dst + 4 * C, ld, h->cbuf + (size_t)S * C, C, C, rows, st))) return rc;
+    if ((rc = copy2d(dst + 5 * C, ld, h->hbuf, C, C, rows, st))) return rc;
+    if ((rc = copy2d(dst + 6 * C, ld, h->mbuf, C, C, rows, st))) return rc;
+    if ((rc = copy2d(dst + 7 * C, ld, h->rbuf + (size_t)S * R, R, R, rows, st))) return rc;
+  } else {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, dst);
+    bool on_device = (e == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged));
+    if (e != cudaSuccess) cudaGetLastError();
+    if (on_device) {
+      CUDA_TRY(cudaMemset2DAsync(dst + 4 * C, ld * sizeof(float), 0, (size_t)3 * C * sizeof(float), rows, st));
+    } else {
+      CUDA_TRY(cudaStreamSynchronize(st));
+      for (size_t r = 0; r < rows; ++r) memset(dst + r * ld + 4 * C, 0, (size_t)3 * C * sizeof(float));
+    }
+    if ((rc = copy2d(dst, ld, h->dgifo, 4 * C, 4 * C, rows, st))) return rc;
+    if ((rc = copy2d(dst + 7 * C, ld, h->dr, R, R, rows, st))) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,83 @@
+// Internal (non-ABI) interface between the host engine and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace lstmp {
+
+constexpr int kMaxGroupsHost = 8;
+
+// Work decomposition of one persistent launch (shared by forward and backward).
+//   grid = ngroups * ctas_per_group co-resident CTAs (cooperative launch, 1 CTA / SM).
+//   Group g owns streams [g*Sg, (g+1)*Sg); inside a group CTA j owns
+//     cells      [j*cpc, j*cpc+cpc)      (gate rows of W_gifo_r, cell-wise elementwise work)
+//     r columns  [j*rpc, j*rpc+rpc)      (rows of W_r_m for the projection, forward only)
+//     a `piece`-float slice of the group's flattened [Sg x R] d_r block (backward reduce-scatter).
+struct Decomp {
+  int ngroups, ctas_per_group, Sg, cpc, rpc, piece, KC;
+};
+
+struct FwdParams {
+  int I, C, R, S, T;
+  Decomp d;
+  // dynamic shared memory carve-up (offsets in floats)
+  int off_wr, ldwr, off_wm, ldwm, off_xbuf, off_red, ldred, off_cprev, off_peep;
+  const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
+  float *gifo;   // [T*S x 4C]  in: x*W_x^T + bias (pre-activations); out: g,i,f,o activations
+  float *cbuf;   // [(T+1)*S x C]  block 0 = c_0
+  float *hbuf;   // [T*S x C]
+  float *mbuf;   // [T*S x C]
+  float *rbuf;   // [(T+1)*S x R]  block 0 = r_0
+  float *out;    // [T*S x R], row stride ld_out
+  long long ld_out;
+  float *state_c;  // [S x C]
+  float *state_r;  // [S x R]
+  unsigned *bar;   // [ngroups]
+  unsigned bar_base[kMaxGroupsHost];
+};
+
+struct BwdParams {
+  int I, C, R, S, T;
+  Decomp d;
+  int off_wr, ldwr, off_wmt, ldwmt, off_xbuf, off_red, ldred, off_dgn, ldd, off_dcn, off_acc7, off_peep;
+  const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
+  const float *gifo, *cbuf, *hbuf;
+  const float *out_diff;
+  long long ld_od;
+  float *dgifo;        // [T*S x 4C]
+  float *dr;           // [T*S x R]
+  float *scratch;      // [ngroups][ctas_per_group][Sg*R] partial d_r
+  float *small_grads;  // [ngroups][7C]: bias(4C) | peephole_i | peephole_f | peephole_o
+  unsigned *bar;
+  unsigned bar_base[kMaxGroupsHost];
+};
+
+size_t fwd_smem_floats(int C, int R, const Decomp& d, FwdParams* p);
+size_t bwd_smem_floats(int C, int R, const Decomp& d, BwdParams* p);
+cudaError_t launch_fwd(const FwdParams& p, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_bwd(const BwdParams& p, size_t smem_bytes, cudaStream_t stream);
+cudaError_t set_kernel_smem_limits(size_t fwd_bytes, size_t bwd_bytes);
+int fwd_barriers(int T);
+int bwd_barriers(int T);
+
+// C[M x N] = alpha * op(A) * op(B) + beta * C (+ bias[n] broadcast over rows), row-major with
+// leading dimensions; op(A) is M x K, op(B) is K x N.  tA/tB: 0 = as stored, 1 = transposed.
+cudaError_t launch_gemm(float* C, long long ldc, int M, int N, int K, float alpha, const float* A, long long lda,
+                        int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
+                        cudaStream_t stream);
+
+// corr = G + momentum*corr ; param -= lr*corr   over the flat arena
+cudaError_t launch_update(float* params, float* corr, const float* grads, size_t n, float lr, float momentum,
+                          cudaStream_t stream);
+// G[bias | p_i | p_f | p_o] = sum over groups of small_grads
+cudaError_t launch_small_grads(float* g_small /*7C contiguous in the arena*/, const float* small, int ngroups,
+                               int n7c, cudaStream_t stream);
+// zero state rows of flagged streams (flags as bit mask words, by value)
+struct ResetMask {
+  unsigned w[32];
+};
+cudaError_t launch_reset(float* state_c, int C, float* state_r, int R, int S, const ResetMask& m,
+                         cudaStream_t stream);
+// strided 2-D copy helper for set/get of pitched caller matrices is done with cudaMemcpy2DAsync.
+
+}  // namespace lstmp

@@ -1,0 +1,240 @@
+"""ctypes binding of include/lstmp_b200.h.  Thin: every method is one C-ABI call."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+OK, EINVAL, ENODEV, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+# every symbol include/lstmp_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "lstmp_b200_abi_version", "lstmp_b200_last_error", "lstmp_b200_create", "lstmp_b200_destroy",
+    "lstmp_b200_clone", "lstmp_b200_num_params", "lstmp_b200_set_params", "lstmp_b200_get_params",
+    "lstmp_b200_get_flat", "lstmp_b200_set_flat", "lstmp_b200_arena", "lstmp_b200_get_state",
+    "lstmp_b200_set_state", "lstmp_b200_reset", "lstmp_b200_propagate", "lstmp_b200_backpropagate",
+    "lstmp_b200_update", "lstmp_b200_allreduce_grads_nccl", "lstmp_b200_get_info", "lstmp_b200_get_record",
+    "lstmp_b200_timing_enable", "lstmp_b200_timing_read",
+]
+
+TIMING_KINDS = ["input_gemm", "fwd_recurrent", "bwd_recurrent", "in_diff_gemm", "wgrad_gemms", "small_grads",
+                "update", "reset"]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("lstmp_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Info(ctypes.Structure):
+    _fields_ = [
+        ("input_dim", ctypes.c_int), ("cell_dim", ctypes.c_int), ("recur_dim", ctypes.c_int),
+        ("num_stream", ctypes.c_int), ("max_frames", ctypes.c_int), ("sm_count", ctypes.c_int),
+        ("ngroups", ctypes.c_int), ("ctas_per_group", ctypes.c_int), ("streams_per_group", ctypes.c_int),
+        ("cells_per_cta", ctypes.c_int), ("rcols_per_cta", ctypes.c_int),
+        ("fwd_smem_bytes", ctypes.c_size_t), ("bwd_smem_bytes", ctypes.c_size_t),
+        ("workspace_bytes", ctypes.c_size_t), ("kernel_launches", ctypes.c_ulonglong),
+        ("gemm_backend", ctypes.c_int),
+    ]
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [("ms", ctypes.c_double * 8), ("count", ctypes.c_ulonglong * 8)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "_lib", "liblstmp_b200.so")
+
+
+def load_library():
+    """Load the CUDA engine.  Fails loudly when it has not been built -- there is no other path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise EngineError(ENODEV, "%s not built; run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    L = ctypes.CDLL(path)
+    vp, sz, fp, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int
+    L.lstmp_b200_abi_version.restype = ci
+    L.lstmp_b200_last_error.restype = ctypes.c_char_p
+    L.lstmp_b200_create.argtypes = [ci, ci, ci, ci, ci, ci, ctypes.POINTER(vp)]
+    L.lstmp_b200_destroy.argtypes = [vp]
+    L.lstmp_b200_clone.argtypes = [vp, ctypes.POINTER(vp)]
+    L.lstmp_b200_num_params.argtypes = [vp, ctypes.POINTER(sz)]
+    L.lstmp_b200_set_params.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, sz, vp]
+    L.lstmp_b200_get_params.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, sz, vp]
+    L.lstmp_b200_get_flat.argtypes = [vp, ci, vp, vp]
+    L.lstmp_b200_set_flat.argtypes = [vp, ci, vp, vp]
+    L.lstmp_b200_arena.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(sz)]
+    L.lstmp_b200_get_state.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.lstmp_b200_set_state.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.lstmp_b200_reset.argtypes = [vp, vp, ci, vp]
+    L.lstmp_b200_propagate.argtypes = [vp, vp, sz, vp, sz, ci, vp]
+    L.lstmp_b200_backpropagate.argtypes = [vp, vp, sz, vp, sz, vp, sz, ci, vp]
+    L.lstmp_b200_update.argtypes = [vp, fp, fp, vp]
+    L.lstmp_b200_allreduce_grads_nccl.argtypes = [vp, vp, vp]
+    L.lstmp_b200_get_info.argtypes = [vp, ctypes.POINTER(Info)]
+    L.lstmp_b200_get_record.argtypes = [vp, ci, vp, sz, vp]
+    L.lstmp_b200_timing_enable.argtypes = [vp, ci]
+    L.lstmp_b200_timing_read.argtypes = [vp, ctypes.POINTER(Timing)]
+    for name in ABI_SYMBOLS:
+        f = getattr(L, name)
+        if name not in ("lstmp_b200_last_error",):
+            f.restype = ci
+    _LIB = L
+    return L
+
+
+def _chk(rc):
+    if rc != 0:
+        raise EngineError(rc, load_library().lstmp_b200_last_error().decode("utf-8", "replace"))
+
+
+class _CudaArray:
+    """__cuda_array_interface__ view of an engine-owned device arena (zero copy into torch)."""
+
+    def __init__(self, ptr, n, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {
+            "shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+class Engine:
+    """One LstmProjectedStreams layer resident on one B200."""
+
+    def __init__(self, input_dim, cell_dim, recur_dim, num_stream, max_frames, device=0):
+        L = load_library()
+        h = ctypes.c_void_p()
+        _chk(L.lstmp_b200_create(input_dim, cell_dim, recur_dim, num_stream, max_frames, device, ctypes.byref(h)))
+        self._h = h
+        self.I, self.C, self.R, self.S, self.Tmax = input_dim, cell_dim, recur_dim, num_stream, max_frames
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().lstmp_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream():
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @property
+    def num_params(self):
+        n = ctypes.c_size_t()
+        _chk(load_library().lstmp_b200_num_params(self._h, ctypes.byref(n)))
+        return n.value
+
+    def info(self):
+        i = Info()
+        _chk(load_library().lstmp_b200_get_info(self._h, ctypes.byref(i)))
+        return {k: getattr(i, k) for k, _ in Info._fields_}
+
+    # ---- flat arenas (GetParams order) -------------------------------------------------
+    def set_flat(self, which, tensor_or_array):
+        import numpy as np
+        import torch
+        t = tensor_or_array
+        if isinstance(t, np.ndarray):
+            t = np.ascontiguousarray(t, dtype=np.float32)
+            assert t.size == self.num_params
+            ptr = t.ctypes.data
+        else:
+            t = t.contiguous().float()
+            assert t.numel() == self.num_params
+            ptr = t.data_ptr()
+        _chk(load_library().lstmp_b200_set_flat(self._h, which, ctypes.c_void_p(ptr), self._stream()))
+
+    def get_flat(self, which):
+        import numpy as np
+        out = np.empty(self.num_params, np.float32)
+        _chk(load_library().lstmp_b200_get_flat(self._h, which, ctypes.c_void_p(out.ctypes.data), self._stream()))
+        return out
+
+    def arena_tensor(self, which):
+        """Zero-copy torch view of arena `which` (0 params, 1 momentum-accumulated, 2 fresh grads)."""
+        import torch
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _chk(load_library().lstmp_b200_arena(self._h, which, ctypes.byref(p), ctypes.byref(n)))
+        return torch.as_tensor(_CudaArray(p.value, n.value, self), device="cuda:%d" % self.device)
+
+    # ---- carried state -------------------------------------------------------------------
+    def get_state(self):
+        import numpy as np
+        c = np.empty((self.S, self.C), np.float32)
+        r = np.empty((self.S, self.R), np.float32)
+        _chk(load_library().lstmp_b200_get_state(self._h, ctypes.c_void_p(c.ctypes.data), self.C,
+                                                 ctypes.c_void_p(r.ctypes.data), self.R, self._stream()))
+        return c, r
+
+    def set_state(self, c, r):
+        import numpy as np
+        c = np.ascontiguousarray(c, np.float32)
+        r = np.ascontiguousarray(r, np.float32)
+        assert c.shape == (self.S, self.C) and r.shape == (self.S, self.R)
+        _chk(load_library().lstmp_b200_set_state(self._h, ctypes.c_void_p(c.ctypes.data), self.C,
+                                                 ctypes.c_void_p(r.ctypes.data), self.R, self._stream()))
+
+    def reset(self, flags):
+        import numpy as np
+        f = np.ascontiguousarray(flags, np.int32)
+        _chk(load_library().lstmp_b200_reset(self._h, ctypes.c_void_p(f.ctypes.data), int(f.size), self._stream()))
+
+    # ---- hot path: device tensors (torch) -------------------------------------------------
+    @staticmethod
+    def _mat(t, cols, name):
+        if not t.is_cuda or t.dtype.__str__() != "torch.float32" or t.dim() != 2 or t.shape[1] != cols or (
+                t.shape[0] > 1 and t.stride(1) != 1):
+            raise EngineError(EINVAL, "%s must be a CUDA float32 [rows x %d] matrix with unit column stride" % (name, cols))
+        return ctypes.c_void_p(t.data_ptr()), (t.stride(0) if t.shape[0] > 1 else max(cols, t.stride(0)))
+
+    def propagate(self, x, out):
+        px, ldx = self._mat(x, self.I, "in")
+        po, ldo = self._mat(out, self.R, "out")
+        if out.shape[0] != x.shape[0]:
+            raise EngineError(EINVAL, "out rows != in rows")
+        _chk(load_library().lstmp_b200_propagate(self._h, px, ldx, po, ldo, x.shape[0], self._stream()))
+        self._rows = x.shape[0]
+
+    def backpropagate(self, x, out_diff, in_diff=None):
+        px, ldx = self._mat(x, self.I, "in")
+        pod, ldod = self._mat(out_diff, self.R, "out_diff")
+        if in_diff is not None:
+            pid, ldid = self._mat(in_diff, self.I, "in_diff")
+        else:
+            pid, ldid = None, 0
+        _chk(load_library().lstmp_b200_backpropagate(self._h, px, ldx, pod, ldod, pid, ldid, x.shape[0], self._stream()))
+
+    def update(self, learn_rate, momentum):
+        _chk(load_library().lstmp_b200_update(self._h, float(learn_rate), float(momentum), self._stream()))
+
+    def timing_enable(self, on=True):
+        _chk(load_library().lstmp_b200_timing_enable(self._h, 1 if on else 0))
+
+    def timing_read(self):
+        """{kind: (total_ms, launches)} since the last read (device-side CUDA events)."""
+        t = Timing()
+        _chk(load_library().lstmp_b200_timing_read(self._h, ctypes.byref(t)))
+        return {k: (t.ms[i], int(t.count[i])) for i, k in enumerate(TIMING_KINDS)}
+
+    def get_record(self, backward=False):
+        import numpy as np
+        T = self._last_rows() // self.S
+        W = 7 * self.C + self.R
+        out = np.empty((T * self.S, W), np.float32)
+        _chk(load_library().lstmp_b200_get_record(self._h, 1 if backward else 0, ctypes.c_void_p(out.ctypes.data), W,
+                                                  self._stream()))
+        return out
+
+    def _last_rows(self):
+        return getattr(self, "_rows", self.Tmax * self.S)

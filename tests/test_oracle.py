@@ -169,3 +169,24 @@ def test_oracle_bad_shape(oracle_mod):
     o = oracle_mod.Oracle(4, 4, 4, 3, np.float32)
     with pytest.raises(ValueError):
         o.propagate(np.zeros((4, 4), np.float32))  # 4 rows not a multiple of S=3 (LPS.h:225)
+
+
+def test_oracle_reproduces_golden(oracle_mod):
+    g = np.load(os.path.join(GOLD, "lstmp_small.npz"))
+    I, C, R, S, T = [int(v) for v in g["dims"]]
+    o = oracle_mod.Oracle(I, C, R, S, np.float32)
+    o.set_params(g["params"])
+    for n in range(int(g["nchunks"])):
+        o.reset(g["flags"][n])
+        out = o.propagate(g["x"][n])
+        ind = o.backpropagate(g["x"][n], g["out_diff"][n], float(g["momentum"]))
+        o.update(float(g["lr"]))
+        for a, b in ((out, g["out"][n]), (ind, g["in_diff"][n]), (o.get_grads(), g["corr"][n]),
+                     (o.get_params(), g["params_after"][n]), (o.get_state(), g["state"][n])):
+            assert np.abs(a - b).max() <= 1e-6 * max(np.abs(b).max(), 1e-30)
+    # and the fp64 twin agrees with the stored fp32 vectors to fp32 accuracy
+    o64 = oracle_mod.Oracle(I, C, R, S, np.float64)
+    o64.set_params(g["params"])
+    o64.reset(g["flags"][0])
+    out64 = o64.propagate(g["x"][0])
+    assert np.abs(out64 - g["out"][0]).max() <= 1e-5 * np.abs(out64).max()

@@ -1,0 +1,241 @@
+"""GPU parity: the sm_100a engine, called through the C ABI, against the CPU oracle on the
+same seeded inputs (tolerance 1e-4 relative fp32, BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def klb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import kaldi_lstm_b200 as k
+    k.load_library()  # must exist: no fallback
+    return k
+
+
+@pytest.fixture(scope="module")
+def oracle_blas(oracle_mod):
+    oracle_mod.use_openblas()
+    yield oracle_mod
+    oracle_mod.use_builtin_gemm()
+
+
+def test_tiny_with_record(klb, oracle_mod):
+    from parity_util import run_pair
+    run_pair(klb, oracle_mod, I=8, C=12, R=8, S=3, T=5, nchunks=2, check_record=True, init_state=True, scale=0.3)
+
+
+def test_single_frame_chunks(klb, oracle_mod):
+    from parity_util import run_pair
+    run_pair(klb, oracle_mod, I=8, C=16, R=8, S=2, T=1, nchunks=3, check_record=True, scale=0.3)
+
+
+def test_cfg2_recipe_default(klb, oracle_blas):
+    """BASELINE.json configs[1]: 40-in 800-cell 512-proj, NumStream=4, 20-frame BPTT; two chunks with
+    state carry-over, a Reset on a subset of streams, momentum 0.9."""
+    from parity_util import run_pair
+    resets = [None, np.array([0, 1, 0, 1], np.int32), np.array([1, 0, 0, 0], np.int32)]
+    run_pair(klb, oracle_blas, I=40, C=800, R=512, S=4, T=20, nchunks=3, momentum=0.9, lr=1e-3, scale=0.05,
+             resets=resets, seed=3)
+
+
+def test_cfg2_paramscale_001(klb, oracle_blas):
+    """ParamScale 0.01 and lr 1e-5 exactly as the shipped recipe (google/nnet.proto:3, train_lstm_streams.sh:3-8)."""
+    from parity_util import run_pair
+    run_pair(klb, oracle_blas, I=40, C=800, R=512, S=4, T=20, nchunks=2, momentum=0.9, lr=1e-5, scale=0.01, seed=4,
+             od_scale=0.01)
+
+
+def test_cfg1_single_stream_100_frames(klb, oracle_blas):
+    """BASELINE.json configs[0] shape: S=1, one utterance x 100 frames (the standard/ LstmProjected case,
+    standard/nnet/nnet-lstm-projected.h:222-466, is the S=1 special case of the streams component)."""
+    from parity_util import run_pair
+    run_pair(klb, oracle_blas, I=40, C=800, R=512, S=1, T=100, nchunks=1, momentum=0.0, scale=0.05, seed=5)
+
+
+def test_cfg3_layer1_s64(klb, oracle_blas):
+    from parity_util import run_pair
+    run_pair(klb, oracle_blas, I=40, C=800, R=512, S=64, T=20, nchunks=2, momentum=0.9, scale=0.05, seed=6,
+             resets=[None, (np.arange(64) % 3 == 0).astype(np.int32)])
+
+
+def test_cfg3_layer2_s64_input512(klb, oracle_blas):
+    from parity_util import run_pair
+    run_pair(klb, oracle_blas, I=512, C=800, R=512, S=64, T=20, nchunks=1, momentum=0.9, scale=0.03, seed=7)
+
+
+def test_cfg4_per_gpu_shape_s32(klb, oracle_blas):
+    from parity_util import run_pair
+    run_pair(klb, oracle_blas, I=40, C=800, R=512, S=32, T=20, nchunks=1, scale=0.05, seed=8)
+
+
+def test_pitched_matrices_and_null_in_diff(klb, oracle_mod):
+    """in/out/out_diff/in_diff live in Nnet-owned pitched CuMatrix buffers (stride_ > num_cols_,
+    cu-matrix.cc:67-73); in_diff may be absent for the first trainable layer."""
+    from parity_util import run_pair
+    run_pair(klb, oracle_mod, I=40, C=64, R=32, S=4, T=6, nchunks=2, pad=12, scale=0.2, seed=9)
+    run_pair(klb, oracle_mod, I=40, C=64, R=32, S=4, T=6, nchunks=1, want_in_diff=False, scale=0.2, seed=10)
+
+
+def test_cell_clamp_saturation(klb, oracle_mod):
+    """|c| driven past 50: forward clamps (LPS.h:296-297), backward ignores the clamp (LPS.h:424-428)."""
+    from parity_util import run_pair
+    I, C, R, S, T = 8, 16, 8, 2, 8
+    flat = oracle_mod.init_params(I, C, R, 0.3, 77)
+    a, b, _ = oracle_mod.param_slices(I, C, R)["bias"]
+    flat[a:b] = 4.0
+    worst, comp, o = run_pair(klb, oracle_mod, I, C, R, S, T, nchunks=1, flat=flat, init_state=True, seed=11,
+                              check_record=True)
+    # make the state large and run again: cells must hit the clamp on both sides
+    st = np.zeros((S, 7 * C + R), np.float32)
+    st[:, 4 * C:5 * C] = 49.9
+    o.set_state(st)
+    comp.engine.set_state(st[:, 4 * C:5 * C], st[:, 7 * C:])
+    import torch
+    x = np.random.RandomState(1).randn(T * S, I).astype(np.float32)
+    out = comp.Propagate(torch.from_numpy(x).cuda())
+    ref = o.propagate(x)
+    from parity_util import assert_close
+    assert_close(out.cpu().numpy(), ref, "saturated out")
+    rec = comp.engine.get_record(False)
+    assert np.abs(rec[:, 4 * C:5 * C]).max() == 50.0
+
+
+@pytest.mark.parametrize("ngroups", [1, 2, 4])
+def test_stream_group_decompositions(klb, oracle_blas, ngroups, monkeypatch):
+    """The same maths under every work decomposition the engine can pick."""
+    from parity_util import run_pair
+    monkeypatch.setenv("LSTMP_B200_NGROUPS", str(ngroups))
+    _, comp, _ = run_pair(klb, oracle_blas, I=40, C=256, R=128, S=64, T=6, nchunks=2, scale=0.08, seed=12 + ngroups)
+    assert comp.engine.info()["ngroups"] == ngroups
+
+
+def test_few_ctas(klb, oracle_mod, monkeypatch):
+    """Multi-pass tile loops: few CTAs with many cells each."""
+    from parity_util import run_pair
+    monkeypatch.setenv("LSTMP_B200_MAX_CTAS", "5")
+    run_pair(klb, oracle_mod, I=16, C=100, R=36, S=20, T=4, nchunks=2, scale=0.2, seed=21, check_record=True)
+
+
+def test_growing_chunk_length(klb, oracle_mod):
+    """The reference resizes its buffers per call (LPS.h:230); the mirror re-creates the engine."""
+    from parity_util import run_pair
+    run_pair(klb, oracle_mod, I=8, C=16, R=8, S=2, T=9, nchunks=1, Tmax=4, scale=0.3, seed=22)
+
+
+def test_golden_fixture(klb):
+    """Committed golden vectors (tests/golden/make_golden.py): engine vs stored oracle outputs."""
+    import torch
+    from parity_util import assert_close
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lstmp_small.npz"))
+    I, C, R, S, T = [int(v) for v in g["dims"]]
+    comp = klb.LstmProjectedStreams(I, R, max_frames=T)
+    comp.InitData("<CellDim> %d <NumStream> %d" % (C, S))
+    comp.SetParams(g["params"])
+    comp.SetTrainOptions(klb.NnetTrainOptions(float(g["lr"]), float(g["momentum"])))
+    for n in range(int(g["nchunks"])):
+        comp.Reset(list(g["flags"][n]))
+        x = torch.from_numpy(g["x"][n]).cuda()
+        out = comp.Propagate(x)
+        in_diff = comp.Backpropagate(x, out, torch.from_numpy(g["out_diff"][n]).cuda())
+        comp.Update()
+        assert_close(out.cpu().numpy(), g["out"][n], "golden out %d" % n)
+        assert_close(in_diff.cpu().numpy(), g["in_diff"][n], "golden in_diff %d" % n)
+        assert_close(comp.GetGradients(), g["corr"][n], "golden corr %d" % n)
+        assert_close(comp.GetParams(), g["params_after"][n], "golden params %d" % n)
+
+
+def test_error_behaviour(klb):
+    import torch
+    comp = klb.LstmProjectedStreams(8, 8)
+    with pytest.raises(RuntimeError):  # KALDI_ERR on unknown token (LPS.h:70)
+        comp.InitData("<CellDim> 16 <NumStreams> 2")
+    comp.InitData("<CellDim> 16 <NumStream> 3")
+    with pytest.raises(AssertionError):  # LPS.h:225
+        comp.Propagate(torch.zeros((4, 8), device="cuda"))
+    with pytest.raises(AssertionError):  # LPS.h:214
+        comp.Reset([0, 1])
+    with pytest.raises(klb.EngineError) as ei:
+        comp.engine.backpropagate(torch.zeros((3, 8), device="cuda"), torch.zeros((3, 8), device="cuda"))
+    assert ei.value.code == -4  # ESTATE: no propagate yet
+    with pytest.raises(klb.EngineError):
+        klb.Engine(10, 16, 8, 2, 4)  # input_dim % 4 != 0
+    with pytest.raises(klb.EngineError):
+        comp.engine.propagate(torch.zeros((3, 8)), torch.zeros((3, 8), device="cuda"))  # host tensor
+
+
+def test_copy_is_deep(klb, oracle_mod):
+    import torch
+    comp = klb.LstmProjectedStreams(8, 8)
+    comp.InitData("<CellDim> 16 <NumStream> 2 <ParamScale> 0.3", seed=5)
+    x = torch.randn(6, 8, device="cuda")
+    comp.Propagate(x)
+    twin = comp.Copy()
+    a = comp.Propagate(x).cpu().numpy()
+    b = twin.Propagate(x).cpu().numpy()
+    np.testing.assert_array_equal(a, b)  # same params AND same carried state
+    twin.SetParams(np.zeros(twin.NumParams(), np.float32))
+    assert np.abs(comp.GetParams()).max() > 0
+
+
+# ---- size-independent properties at BASELINE.json's full shapes -----------------------------
+def _full(klb, S=64, I=40, seed=0):
+    import torch
+    comp = klb.LstmProjectedStreams(I, 512)
+    comp.InitData("<CellDim> 800 <NumStream> %d <ParamScale> 0.05" % S, seed=seed)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(20 * S, I, device="cuda", generator=g)
+    od = torch.randn(20 * S, 512, device="cuda", generator=g) * 0.1
+    return comp, x, od
+
+
+def test_full_size_determinism_and_linearity(klb):
+    """Run-to-run bit determinism (no atomics anywhere) and linearity of the backward pass in out_diff."""
+    import torch
+    comp, x, od = _full(klb)
+    twin = comp.Copy()
+    out1 = comp.Propagate(x)
+    d1 = comp.Backpropagate(x, out1, od)
+    g1 = comp.engine.get_flat(2)
+    out2 = twin.Propagate(x)
+    d2 = twin.Backpropagate(x, out2, od * 2.0)
+    g2 = twin.engine.get_flat(2)
+    assert torch.equal(out1, out2)
+    assert np.abs(g2 - 2.0 * g1).max() <= 2e-5 * np.abs(g2).max()
+    assert (d2 - 2.0 * d1).abs().max().item() <= 2e-5 * d2.abs().max().item()
+    # bitwise repeatability
+    third = comp.Copy()
+    third.engine.set_state(*twin.engine.get_state())
+    comp2, _, _ = _full(klb)
+    o_a = comp2.Propagate(x)
+    da = comp2.Backpropagate(x, o_a, od)
+    assert torch.equal(o_a, out1) and torch.equal(da, d1)
+    np.testing.assert_array_equal(comp2.engine.get_flat(2), g1)
+
+
+def test_full_size_zero_out_diff_and_reset(klb):
+    import torch
+    comp, x, od = _full(klb, S=4)
+    out = comp.Propagate(x)
+    d = comp.Backpropagate(x, out, torch.zeros_like(od))
+    assert d.abs().max().item() == 0.0
+    assert np.abs(comp.engine.get_flat(2)).max() == 0.0
+    # Reset(all ones) == fresh component: second chunk equals the first
+    comp.Reset([1] * 4)
+    out2 = comp.Propagate(x)
+    assert torch.equal(out, out2)
+    # without reset the carried state changes the result
+    out3 = comp.Propagate(x)
+    assert not torch.equal(out3, out2)
+    # zero momentum, one update: params move by exactly -lr * G
+    comp.SetTrainOptions(klb.NnetTrainOptions(0.5, 0.0))
+    before = comp.GetParams()
+    comp.Backpropagate(x, out3, od)
+    G = comp.engine.get_flat(2)
+    comp.Update()
+    np.testing.assert_allclose(comp.GetParams(), before - 0.5 * G, rtol=0, atol=1e-6)
