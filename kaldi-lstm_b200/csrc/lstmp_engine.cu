@@ -603,3 +603,24 @@ extern "C" int lstmp_b200_get_record(lstmp_b200_handle_t h, int backward, float*
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
+
+extern "C" int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, int N, int K, float alpha,
+                                     const float* A, size_t lda, int tA, const float* B, size_t ldb, int tB, float beta,
+                                     const float* bias, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backend == 0) {
+    CUDA_TRY(launch_gemm_simt(C, (long long)ldc, M, N, K, alpha, A, (long long)lda, tA, B, (long long)ldb, tB, beta,
+                              bias, st));
+    return 0;
+  }
+#ifdef LSTMP_HAVE_TC_GEMM
+  if (backend == 1) {
+    bool handled = false;
+    CUDA_TRY(launch_gemm_tc(C, (long long)ldc, M, N, K, alpha, A, (long long)lda, tA, B, (long long)ldb, tB, beta, bias,
+                            st, &handled));
+    if (!handled) return fail(LSTMP_B200_EUNSUPPORTED, "tcgen05 GEMM does not handle this shape/alignment");
+    return 0;
+  }
+#endif
+  return fail(LSTMP_B200_EUNSUPPORTED, "unknown GEMM backend %d", backend);
+}

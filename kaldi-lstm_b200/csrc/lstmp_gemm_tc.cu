@@ -1,0 +1,350 @@
+// tcgen05 (5th-gen tensor core) GEMM with FP32-faithful 3xTF32 split arithmetic, sm_100a only.
+//
+//   C[M x N] = alpha * op(A) * op(B) + beta * C (+ bias[n])       fp32 in, fp32 out
+//
+// Used for the contractions OUTSIDE the time loop (CuMatrixBase::AddMatMat call sites
+// LPS.h:246, :457, :468, :471, :486 of the reference), which are the dense stream-batched GEMMs.
+//
+// Precision: the path must match the reference's fp32 SGEMM to 1e-4, and single-pass TF32
+// (10-bit mantissa) does not.  Every fp32 operand x is split on the fly into
+//     hi = x & 0xffffe000   (exactly representable in TF32)
+//     lo = x - hi           (exact in fp32; its own TF32 truncation error is ~2^-21 |x|)
+// and the product is accumulated in FP32 in TMEM as  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b.
+//
+// Structure of one CTA (288 threads), one 128 x BN output tile:
+//   warps 0-7  : loader/transform -- coalesced LDG.128 of the fp32 operands (either storage
+//                order), split into hi/lo, STS.128 into UMMA canonical no-swizzle shared-memory
+//                tiles (K-major for k-contiguous sources, MN-major for m/n-contiguous sources, so no
+//                transposition is ever needed), fence.proxy.async, mbarrier arrive.  After the
+//                main loop the same warps run the epilogue: tcgen05.ld -> alpha/beta/bias -> STG.
+//   warp 8     : TMEM allocation; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN,
+//                K=8) x 12 per 32-deep K block and tcgen05.commit onto the stage's "empty"
+//                mbarrier / the accumulator-ready mbarrier.
+// 3-stage shared-memory ring, mbarrier full/empty handshakes, accumulator in TMEM.
+#include "lstmp_common.cuh"
+#include "lstmp_kernels.h"
+
+namespace lstmp {
+
+namespace tc {
+constexpr int BM = 128;
+constexpr int BK = 32;        // fp32 elements per stage along K (= 4 MMAs of K=8)
+constexpr int NSTAGE = 3;
+constexpr int LOADERS = 256;  // warps 0-7
+constexpr int THREADS = LOADERS + 32;
+
+// Shared-memory tile geometry (bytes).  rows = BM or BN.
+// K-major  : off(r,k) = (k/4)*LBO + (r/8)*128 + (r%8)*16 + (k%4)*4     LBO = rows*16 + 16 (odd # of 16B units)
+// MN-major : off(r,k) = (r/4)*SBO + (r%4)*4 + (k%8)*16 + (k/8)*LBO      SBO = 144, LBO = (rows/4)*144
+__host__ __device__ constexpr uint32_t kmaj_lbo(int rows) { return rows * 16 + 16; }
+__host__ __device__ constexpr uint32_t kmaj_bytes(int rows) { return (BK / 4) * kmaj_lbo(rows); }
+__host__ __device__ constexpr uint32_t mnmaj_sbo() { return 144; }
+__host__ __device__ constexpr uint32_t mnmaj_lbo(int rows) { return (rows / 4) * mnmaj_sbo(); }
+__host__ __device__ constexpr uint32_t mnmaj_bytes(int rows) { return (BK / 8) * mnmaj_lbo(rows); }
+__host__ __device__ constexpr uint32_t tile_bytes(int rows, bool mn) {
+  return ((mn ? mnmaj_bytes(rows) : kmaj_bytes(rows)) + 127u) & ~127u;
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
+  // layout_type SWIZZLE_NONE=0 [61,64)
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// One operand's loader state: RN float4 units per thread per K block.
+template <int ROWS, bool MN>
+struct Loader {
+  static constexpr int UNITS = ROWS * (BK / 4) / LOADERS;  // float4 units per thread
+  float4 v[UNITS];
+
+  // element coordinates of unit u: row r (M or N index inside the tile) and k (inside the K block);
+  // a unit is 4 consecutive k (K-major source) or 4 consecutive rows (MN-major source).
+  __device__ __forceinline__ void load(const float* __restrict__ src, long long ld, int row0, int nrows, int k0,
+                                       int K, int tid) {
+#pragma unroll
+    for (int i = 0; i < UNITS; ++i) {
+      const int u = tid + i * LOADERS;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!MN) {
+        const int kc = u % (BK / 4), r = u / (BK / 4);
+        const int gr = row0 + r, gk = k0 + 4 * kc;
+        if (gr < nrows && gk < K) x = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gk));
+      } else {
+        const int rg = u % (ROWS / 4), k = u / (ROWS / 4);
+        const int gr = row0 + 4 * rg, gk = k0 + k;
+        if (gr < nrows && gk < K) x = __ldg(reinterpret_cast<const float4*>(src + (size_t)gk * ld + gr));
+      }
+      v[i] = x;
+    }
+  }
+  __device__ __forceinline__ void store(uint8_t* hi, uint8_t* lo, int tid) const {
+#pragma unroll
+    for (int i = 0; i < UNITS; ++i) {
+      const int u = tid + i * LOADERS;
+      uint32_t off;
+      if (!MN) {
+        const int kc = u % (BK / 4), r = u / (BK / 4);
+        off = kc * kmaj_lbo(ROWS) + (r >> 3) * 128 + (r & 7) * 16;
+      } else {
+        const int rg = u % (ROWS / 4), k = u / (ROWS / 4);
+        off = rg * mnmaj_sbo() + (k & 7) * 16 + (k >> 3) * mnmaj_lbo(ROWS);
+      }
+      const float4 x = v[i];
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+      h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+      h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+      h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+      l.x = x.x - h.x;
+      l.y = x.y - h.y;
+      l.z = x.z - h.z;
+      l.w = x.w - h.w;
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+  }
+};
+
+template <int BN, bool A_MN, bool B_MN>
+struct Smem {
+  static constexpr uint32_t A_BYTES = tile_bytes(BM, A_MN);
+  static constexpr uint32_t B_BYTES = tile_bytes(BN, B_MN);
+  static constexpr uint32_t STAGE = 2 * A_BYTES + 2 * B_BYTES;  // A_hi | A_lo | B_hi | B_lo
+  static constexpr uint32_t TOTAL = NSTAGE * STAGE + 1024;       // + barriers / tmem slot / alignment slack
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float alpha,
+               const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float beta,
+               const float* __restrict__ bias) {
+  using SM = Smem<BN, A_MN, B_MN>;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // 128-byte align the tile area
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * SM::STAGE);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* accum_ready = empty + NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = (K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], LOADERS);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) {
+    // TMEM: BN fp32 accumulator columns x 128 lanes (power of two >= 32 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // =============================== loader / transform ==================================
+    Loader<BM, A_MN> la;
+    Loader<BN, B_MN> lb;
+    la.load(A, lda, m0, M, 0, K, tid);
+    lb.load(B, ldb, n0, N, 0, K, tid);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NSTAGE;
+      if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
+      uint8_t* st = tiles + (size_t)s * SM::STAGE;
+      la.store(st, st + SM::A_BYTES, tid);
+      lb.store(st + 2 * SM::A_BYTES, st + 2 * SM::A_BYTES + SM::B_BYTES, tid);
+      if (kb + 1 < nkb) {
+        la.load(A, lda, m0, M, (kb + 1) * BK, K, tid);
+        lb.load(B, ldb, n0, N, (kb + 1) * BK, K, tid);
+      }
+      fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+      mbar_arrive(&full[s]);
+    }
+    // =============================== epilogue ============================================
+    mbar_wait(accum_ready, 0);
+    tc_fence_after();
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = warp >> 2;           // column half
+    const int lane = tid & 31;
+    const int gm = m0 + quad * 32 + lane;
+    constexpr int COLS_PER_WARP = BN / 2;
+#pragma unroll 1
+    for (int c = 0; c < COLS_PER_WARP; c += 16) {
+      const int col = half * COLS_PER_WARP + c;
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, v);
+      if (gm < M) {
+        float* crow = Cm + (size_t)gm * ldc;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int gn = n0 + col + j;
+          if (gn + 3 < N && ((ldc & 3) == 0)) {
+            float4 o = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+            if (beta != 0.f) {
+              float4 cc = *reinterpret_cast<const float4*>(crow + gn);
+              o.x += beta * cc.x; o.y += beta * cc.y; o.z += beta * cc.z; o.w += beta * cc.w;
+            }
+            if (bias) {
+              float4 bb = __ldg(reinterpret_cast<const float4*>(bias + gn));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(crow + gn) = o;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (gn + q < N) {
+                float o = alpha * v[j + q];
+                if (beta != 0.f) o += beta * crow[gn + q];
+                if (bias) o += bias[gn + q];
+                crow[gn + q] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =============================== MMA issuer (warp 8) ==================================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+    // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t tiles_s = smem_u32(tiles);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NSTAGE;
+      mbar_wait(&full[s], (uint32_t)((kb / NSTAGE) & 1));
+      tc_fence_after();
+      if ((tid & 31) == 0) {
+        const uint32_t a_hi = tiles_s + s * SM::STAGE, a_lo = a_hi + SM::A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
+#pragma unroll
+        for (int j = 0; j < BK / 8; ++j) {
+          // K-major: MMA j covers 16-byte K chunks 2j,2j+1; MN-major: MMA j covers k-group j
+          const uint32_t a_off = A_MN ? j * mnmaj_lbo(BM) : 2 * j * kmaj_lbo(BM);
+          const uint32_t b_off = B_MN ? j * mnmaj_lbo(BN) : 2 * j * kmaj_lbo(BN);
+          const uint32_t a_l = A_MN ? mnmaj_lbo(BM) : kmaj_lbo(BM), a_s = A_MN ? mnmaj_sbo() : 128u;
+          const uint32_t b_l = B_MN ? mnmaj_lbo(BN) : kmaj_lbo(BN), b_s = B_MN ? mnmaj_sbo() : 128u;
+          const uint64_t dah = make_desc(a_hi + a_off, a_l, a_s), dal = make_desc(a_lo + a_off, a_l, a_s);
+          const uint64_t dbh = make_desc(b_hi + b_off, b_l, b_s), dbl = make_desc(b_lo + b_off, b_l, b_s);
+          mma_tf32(tmem_base, dal, dbh, idesc, (kb | j) ? 1u : 0u);  // small terms first
+          mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&empty[s]);                       // frees the stage once these MMAs have read it
+        if (kb == nkb - 1) umma_commit(accum_ready);  // accumulator complete
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
+                              long long lda, const float* B, long long ldb, float beta, const float* bias,
+                              cudaStream_t stream) {
+  using SM = Smem<BN, A_MN, B_MN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!attr_set[dev & 63]) {
+    e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SM::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM), block(THREADS);
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
+                                                                     bias);
+  return cudaGetLastError();
+}
+}  // namespace tc
+
+// tA/tB as in launch_gemm: op(A) is M x K.  tA == 0: A stored [M x K] (k contiguous -> K-major);
+// tA == 1: A stored [K x M] (m contiguous -> MN-major).  op(B) is K x N.  tB == 0: B stored [K x N]
+// (n contiguous -> MN-major); tB == 1: B stored [N x K] (k contiguous -> K-major).
+cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float alpha, const float* A, long long lda,
+                           int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
+                           cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool a_mn = (tA != 0), b_mn = (tB == 0);
+  // 128-bit loads: contiguous extent and leading dimension multiples of 4 floats, 16-byte bases
+  if (!al16(A) || !al16(B) || (lda & 3) || (ldb & 3)) return cudaSuccess;
+  if ((K & 3) && (!a_mn || !b_mn)) return cudaSuccess;
+  if (a_mn && (M & 3)) return cudaSuccess;
+  if (b_mn && (N & 3)) return cudaSuccess;
+  if (bias && !al16(bias)) return cudaSuccess;
+  if (!al16(C)) return cudaSuccess;
+  *handled = true;
+  const bool small_n = (N <= 64);
+#define LSTMP_TC_CASE(BN_, AMN_, BMN_) \
+  return tc::launch_one<BN_, AMN_, BMN_>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream)
+  if (small_n) {
+    if (!a_mn && !b_mn) LSTMP_TC_CASE(64, false, false);
+    if (!a_mn && b_mn) LSTMP_TC_CASE(64, false, true);
+    if (a_mn && !b_mn) LSTMP_TC_CASE(64, true, false);
+    LSTMP_TC_CASE(64, true, true);
+  } else {
+    if (!a_mn && !b_mn) LSTMP_TC_CASE(128, false, false);
+    if (!a_mn && b_mn) LSTMP_TC_CASE(128, false, true);
+    if (a_mn && !b_mn) LSTMP_TC_CASE(128, true, false);
+    LSTMP_TC_CASE(128, true, true);
+  }
+#undef LSTMP_TC_CASE
+}
+
+}  // namespace lstmp

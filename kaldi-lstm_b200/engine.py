@@ -14,7 +14,7 @@ ABI_SYMBOLS = [
     "lstmp_b200_get_flat", "lstmp_b200_set_flat", "lstmp_b200_arena", "lstmp_b200_get_state",
     "lstmp_b200_set_state", "lstmp_b200_reset", "lstmp_b200_propagate", "lstmp_b200_backpropagate",
     "lstmp_b200_update", "lstmp_b200_allreduce_grads_nccl", "lstmp_b200_get_info", "lstmp_b200_get_record",
-    "lstmp_b200_timing_enable", "lstmp_b200_timing_read",
+    "lstmp_b200_timing_enable", "lstmp_b200_timing_read", "lstmp_b200_debug_gemm",
 ]
 
 TIMING_KINDS = ["input_gemm", "fwd_recurrent", "bwd_recurrent", "in_diff_gemm", "wgrad_gemms", "small_grads",
@@ -77,6 +77,7 @@ def load_library():
     L.lstmp_b200_allreduce_grads_nccl.argtypes = [vp, vp, vp]
     L.lstmp_b200_get_info.argtypes = [vp, ctypes.POINTER(Info)]
     L.lstmp_b200_get_record.argtypes = [vp, ci, vp, sz, vp]
+    L.lstmp_b200_debug_gemm.argtypes = [ci, vp, sz, ci, ci, ci, fp, vp, sz, ci, vp, sz, ci, fp, vp, vp]
     L.lstmp_b200_timing_enable.argtypes = [vp, ci]
     L.lstmp_b200_timing_read.argtypes = [vp, ctypes.POINTER(Timing)]
     for name in ABI_SYMBOLS:
@@ -238,3 +239,14 @@ class Engine:
 
     def _last_rows(self):
         return getattr(self, "_rows", self.Tmax * self.S)
+
+
+def debug_gemm(backend, C, M, N, K, alpha, A, tA, B, tB, beta=0.0, bias=None):
+    """C = alpha*op(A)*op(B) + beta*C (+bias) with one of the engine's GEMM kernels (torch CUDA tensors)."""
+    import torch
+    L = load_library()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _chk(L.lstmp_b200_debug_gemm(int(backend), ctypes.c_void_p(C.data_ptr()), C.stride(0), M, N, K, float(alpha),
+                                 ctypes.c_void_p(A.data_ptr()), A.stride(0), int(tA), ctypes.c_void_p(B.data_ptr()),
+                                 B.stride(0), int(tB), float(beta),
+                                 ctypes.c_void_p(bias.data_ptr()) if bias is not None else None, st))

@@ -1,0 +1,71 @@
+"""The engine's GEMM kernels (fp32 SIMT and tcgen05 3xTF32) against an fp64 torch product, on
+every operand-order combination the path uses (AddMatMat call sites LPS.h:246,457,468,471,486)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from kaldi_lstm_b200 import engine
+    engine.load_library()
+    return engine
+
+
+def _case(eng, backend, M, N, K, tA, tB, alpha=1.0, beta=0.0, bias=False, pad=0, seed=0):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn((K, M + pad) if tA else (M, K + pad), device="cuda", generator=g)[:, :(M if tA else K)]
+    B = torch.randn((N, K + pad) if tB else (K, N + pad), device="cuda", generator=g)[:, :(K if tB else N)]
+    C = torch.randn((M, N + pad), device="cuda", generator=g)[:, :N]
+    bvec = torch.randn(N, device="cuda", generator=g) if bias else None
+    opA = (A.t() if tA else A).double()
+    opB = (B.t() if tB else B).double()
+    ref = alpha * (opA @ opB) + beta * C.double()
+    if bias:
+        ref = ref + bvec.double()
+    out = C.clone() if pad == 0 else C  # strided view is written in place
+    if pad == 0:
+        out = C.clone()
+    eng.debug_gemm(backend, out, M, N, K, alpha, A, tA, B, tB, beta, bvec)
+    torch.cuda.synchronize()
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    return err
+
+
+SHAPES = [
+    # (M, N, K, tA, tB)  -- the five call sites at cfg-3 sizes
+    (1280, 3200, 40, 0, 1),    # input GEMM  in * W_x^T          (K-major, K-major)
+    (1280, 3200, 512, 0, 1),   # layer-2 input GEMM
+    (1280, 40, 3200, 0, 0),    # in_diff = DGIFO * W_x           (K-major, MN-major), small N
+    (1280, 512, 3200, 0, 0),
+    (3200, 40, 1280, 1, 0),    # G(w_gifo_x) = DGIFO^T * in      (MN-major, MN-major), small N
+    (3200, 512, 1280, 1, 0),   # G(w_gifo_r)
+    (512, 800, 1280, 1, 0),    # G(w_r_m), N not a multiple of the tile
+    (80, 3200, 40, 0, 1),      # cfg-2 sizes (M < tile)
+    (3200, 512, 80, 1, 0),
+    (132, 260, 36, 1, 1),      # ragged everything, (MN-major, K-major)
+    (4, 8, 4, 0, 1),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemm_simt(eng, shape):
+    M, N, K, tA, tB = shape
+    assert _case(eng, 0, M, N, K, tA, tB, alpha=0.7, beta=0.3, bias=True) <= 2e-6
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemm_tcgen05_3xtf32(eng, shape):
+    M, N, K, tA, tB = shape
+    err = _case(eng, 1, M, N, K, tA, tB, alpha=0.7, beta=0.3, bias=True)
+    assert err <= 2e-6, "3xTF32 error %.3e (single-pass TF32 would be ~1e-3)" % err
+
+
+def test_gemm_tcgen05_pitched(eng):
+    assert _case(eng, 1, 1280, 512, 3200, 0, 0, pad=12) <= 2e-6
+    assert _case(eng, 1, 3200, 512, 1280, 1, 0, pad=8) <= 2e-6
