@@ -13,9 +13,9 @@
 //
 // Structure of one CTA (288 threads), one 128 x BN output tile:
 //   warps 0-7  : loader/transform -- coalesced LDG.128 of the fp32 operands (either storage
-//                order), split into hi/lo, STS.128 into UMMA canonical no-swizzle shared-memory
-//                tiles (K-major for k-contiguous sources, MN-major for m/n-contiguous sources, so no
-//                transposition is ever needed), fence.proxy.async, mbarrier arrive.  After the
+//                order; m/n-contiguous sources are transposed in registers), split into hi/lo,
+//                STS.128 into UMMA canonical no-swizzle K-major shared-memory tiles,
+//                fence.proxy.async, mbarrier arrive.  After the
 //                main loop the same warps run the epilogue: tcgen05.ld -> alpha/beta/bias -> STG.
 //   warp 8     : TMEM allocation; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN,
 //                K=8) x 12 per 32-deep K block and tcgen05.commit onto the stage's "empty"
@@ -85,64 +85,99 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// One operand's loader state: RN float4 units per thread per K block.
+// One operand's loader state.  The shared-memory tile is ALWAYS K-major (the layout validated on
+// hardware); a source stored with the M/N index contiguous ("MN-major", e.g. DGIFO^T for the weight
+// gradients) is transposed on the fly in registers: each thread owns a 4(k) x 4(mn) block, loads it with
+// four coalesced LDG.128 along mn and stores four 16-byte K-chunks, one per mn row.
 template <int ROWS, bool MN>
 struct Loader {
-  static constexpr int UNITS = ROWS * (BK / 4) / LOADERS;  // float4 units per thread
-  float4 v[UNITS];
+  static constexpr int UNITS = ROWS * (BK / 4) / LOADERS;              // float4 units per thread (K-major source)
+  static constexpr int NBLK = (ROWS / 4) * (BK / 4);                    // 4x4 blocks per tile (MN-major source)
+  static constexpr int BPT = (NBLK + LOADERS - 1) / LOADERS;            // blocks per thread
+  float4 v[MN ? BPT * 4 : UNITS];
 
-  // element coordinates of unit u: row r (M or N index inside the tile) and k (inside the K block);
-  // a unit is 4 consecutive k (K-major source) or 4 consecutive rows (MN-major source).
   __device__ __forceinline__ void load(const float* __restrict__ src, long long ld, int row0, int nrows, int k0,
                                        int K, int tid) {
+    if (!MN) {
 #pragma unroll
-    for (int i = 0; i < UNITS; ++i) {
-      const int u = tid + i * LOADERS;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!MN) {
+      for (int i = 0; i < UNITS; ++i) {
+        const int u = tid + i * LOADERS;
         const int kc = u % (BK / 4), r = u / (BK / 4);
         const int gr = row0 + r, gk = k0 + 4 * kc;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gr < nrows && gk < K) x = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gk));
-      } else {
-        const int rg = u % (ROWS / 4), k = u / (ROWS / 4);
-        const int gr = row0 + 4 * rg, gk = k0 + k;
-        if (gr < nrows && gk < K) x = __ldg(reinterpret_cast<const float4*>(src + (size_t)gk * ld + gr));
+        v[i] = x;
       }
-      v[i] = x;
+    } else {
+      // blocks of 4 k x 4 mn: block b -> mn-block mb = b % (ROWS/4), k-chunk kc = b / (ROWS/4)
+#pragma unroll
+      for (int blk = 0; blk < BPT; ++blk) {
+        const int b = tid + blk * LOADERS;
+        const int mb = b % (ROWS / 4), kc = b / (ROWS / 4);
+        const int gr = row0 + 4 * mb;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int gk = k0 + 4 * kc + kk;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b < NBLK && gr < nrows && gk < K) x = __ldg(reinterpret_cast<const float4*>(src + (size_t)gk * ld + gr));
+          v[blk * 4 + kk] = x;  // row kk of the block: 4 consecutive mn at k = 4kc+kk
+        }
+      }
     }
   }
+
+  static __device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t off, float4 x) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+    l.x = x.x - h.x;
+    l.y = x.y - h.y;
+    l.z = x.z - h.z;
+    l.w = x.w - h.w;
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+
   __device__ __forceinline__ void store(uint8_t* hi, uint8_t* lo, int tid) const {
+    if (!MN) {
 #pragma unroll
-    for (int i = 0; i < UNITS; ++i) {
-      const int u = tid + i * LOADERS;
-      uint32_t off;
-      if (!MN) {
+      for (int i = 0; i < UNITS; ++i) {
+        const int u = tid + i * LOADERS;
         const int kc = u % (BK / 4), r = u / (BK / 4);
-        off = kc * kmaj_lbo(ROWS) + (r >> 3) * 128 + (r & 7) * 16;
-      } else {
-        const int rg = u % (ROWS / 4), k = u / (ROWS / 4);
-        off = rg * mnmaj_sbo() + (k & 7) * 16 + (k >> 3) * mnmaj_lbo(ROWS);
+        split_store(hi, lo, kc * kmaj_lbo(ROWS) + (r >> 3) * 128 + (r & 7) * 16, v[i]);
       }
-      const float4 x = v[i];
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-      h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-      h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-      h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-      l.x = x.x - h.x;
-      l.y = x.y - h.y;
-      l.z = x.z - h.z;
-      l.w = x.w - h.w;
-      *reinterpret_cast<float4*>(hi + off) = h;
-      *reinterpret_cast<float4*>(lo + off) = l;
+    } else {
+#pragma unroll
+      for (int blk = 0; blk < BPT; ++blk) {
+        const int b = tid + blk * LOADERS;
+        if (b >= NBLK) break;
+        const int mb = b % (ROWS / 4), kc = b / (ROWS / 4);
+        const float4 r0 = v[blk * 4 + 0], r1 = v[blk * 4 + 1], r2 = v[blk * 4 + 2], r3 = v[blk * 4 + 3];
+        // transposed columns: c_i = (k0..k3) at mn = 4mb+i
+        const float4 c0 = make_float4(r0.x, r1.x, r2.x, r3.x);
+        const float4 c1 = make_float4(r0.y, r1.y, r2.y, r3.y);
+        const float4 c2 = make_float4(r0.z, r1.z, r2.z, r3.z);
+        const float4 c3 = make_float4(r0.w, r1.w, r2.w, r3.w);
+        // rotate the store order per lane so the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups
+        const int rot = (mb >> 1) & 3;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int i = (t + rot) & 3;
+          const float4 c = (i == 0) ? c0 : (i == 1) ? c1 : (i == 2) ? c2 : c3;
+          const int r = 4 * mb + i;
+          split_store(hi, lo, kc * kmaj_lbo(ROWS) + (r >> 3) * 128 + (r & 7) * 16, c);
+        }
+      }
     }
   }
 };
 
 template <int BN, bool A_MN, bool B_MN>
 struct Smem {
-  static constexpr uint32_t A_BYTES = tile_bytes(BM, A_MN);
-  static constexpr uint32_t B_BYTES = tile_bytes(BN, B_MN);
+  static constexpr uint32_t A_BYTES = tile_bytes(BM, false);
+  static constexpr uint32_t B_BYTES = tile_bytes(BN, false);
   static constexpr uint32_t STAGE = 2 * A_BYTES + 2 * B_BYTES;  // A_hi | A_lo | B_hi | B_lo
   static constexpr uint32_t TOTAL = NSTAGE * STAGE + 1024;       // + barriers / tmem slot / alignment slack
 };
@@ -253,8 +288,8 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
     // =============================== MMA issuer (warp 8) ==================================
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
     // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);  // both operands K-major in shared memory
     const uint32_t tiles_s = smem_u32(tiles);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % NSTAGE;
@@ -265,11 +300,9 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
         const uint32_t b_hi = a_hi + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
-          // K-major: MMA j covers 16-byte K chunks 2j,2j+1; MN-major: MMA j covers k-group j
-          const uint32_t a_off = A_MN ? j * mnmaj_lbo(BM) : 2 * j * kmaj_lbo(BM);
-          const uint32_t b_off = B_MN ? j * mnmaj_lbo(BN) : 2 * j * kmaj_lbo(BN);
-          const uint32_t a_l = A_MN ? mnmaj_lbo(BM) : kmaj_lbo(BM), a_s = A_MN ? mnmaj_sbo() : 128u;
-          const uint32_t b_l = B_MN ? mnmaj_lbo(BN) : kmaj_lbo(BN), b_s = B_MN ? mnmaj_sbo() : 128u;
+          // MMA j covers the 16-byte K chunks 2j and 2j+1 (K = 8 tf32 per instruction)
+          const uint32_t a_off = 2 * j * kmaj_lbo(BM), b_off = 2 * j * kmaj_lbo(BN);
+          const uint32_t a_l = kmaj_lbo(BM), a_s = 128u, b_l = kmaj_lbo(BN), b_s = 128u;
           const uint64_t dah = make_desc(a_hi + a_off, a_l, a_s), dal = make_desc(a_lo + a_off, a_l, a_s);
           const uint64_t dbh = make_desc(b_hi + b_off, b_l, b_s), dbl = make_desc(b_lo + b_off, b_l, b_s);
           mma_tf32(tmem_base, dal, dbh, idesc, (kb | j) ? 1u : 0u);  // small terms first
