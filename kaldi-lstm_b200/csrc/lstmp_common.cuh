@@ -82,30 +82,35 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 
 // ---------------------------------------------------------------------------------------
 // Group-wide barrier between the co-resident CTAs of one stream group (cooperative launch).
-// Monotonic counter: every CTA adds 1 per barrier; barrier k (1-based) of this launch is
-// complete when counter - base >= k * nctas.  Release/acquire through __threadfence() as
-// cooperative_groups::grid_group::sync() does; wrap-safe signed comparison.
+// One monotonic arrival counter per group: every CTA does one release-ordered RED (+1) and one
+// thread polls the counter with RELAXED loads (an acquire load costs an L1 invalidate per poll),
+// followed by a single acquire fence.  Barrier k of the launch completes when
+// counter - base >= k * nctas (wrap-safe).  Measured ~1.5 us on 148 CTAs; a per-CTA flag array
+// polled by every CTA was slower (hot-line contention), see DESIGN.md.
 // ---------------------------------------------------------------------------------------
 struct GroupBarrier {
   unsigned* counter;
   unsigned target;  // thread 0's running target
   unsigned nctas;
-  __device__ __forceinline__ void init(unsigned* c, unsigned base, unsigned n) {
+  bool off;
+  __device__ __forceinline__ void init(unsigned* c, unsigned base, unsigned n, bool disabled) {
     counter = c;
     target = base;
     nctas = n;
+    off = disabled;
   }
   __device__ __forceinline__ void sync() {
-    __syncthreads();
+    __syncthreads();  // all of this CTA's global writes are ordered before thread 0's release
     if (threadIdx.x == 0) {
       target += nctas;
-      __threadfence();
-      atomicAdd(counter, 1u);
-      unsigned v;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(counter) : "memory");
-      } while (static_cast<int>(v - target) < 0);
-      __threadfence();
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+      if (!off) {
+        unsigned v;
+        do {
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(counter) : "memory");
+        } while (static_cast<int>(v - target) < 0);
+        asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+      }
     }
     __syncthreads();
   }
@@ -133,97 +138,233 @@ __host__ __device__ __forceinline__ int pow2_floor(int x) {
   return p;
 }
 
+// Debug time stamps (build with -DLSTMP_STAMPS and run with LSTMP_B200_DEBUG & 4): thread 0 of CTA 0
+// appends (tag, clock64) pairs to a shared-memory log that is flushed to global memory at kernel end.
+#ifdef LSTMP_STAMPS
+constexpr int kMaxStamps = 384;
+__shared__ long long s_stamp_log[2 * kMaxStamps];
+__shared__ int s_stamp_n;
+__shared__ int s_stamp_on;
+__device__ __forceinline__ void stamp(int tag) {
+  if (threadIdx.x == 0 && s_stamp_on) {
+    int n = s_stamp_n;
+    if (n < kMaxStamps) {
+      s_stamp_log[2 * n] = tag;
+      s_stamp_log[2 * n + 1] = clock64();
+      s_stamp_n = n + 1;
+    }
+  }
+}
+__device__ __forceinline__ void stamp_begin(bool on) {
+  if (threadIdx.x == 0) {
+    s_stamp_on = on ? 1 : 0;
+    s_stamp_n = 0;
+  }
+}
+__device__ __forceinline__ void stamp_flush(long long* dst) {
+  if (threadIdx.x == 0 && s_stamp_on && dst) {
+    long long base = dst[0];
+    int n = s_stamp_n;
+    for (int i = 0; i < n && base + i < 1024; ++i) {
+      dst[2 + 2 * (base + i)] = s_stamp_log[2 * i];
+      dst[3 + 2 * (base + i)] = s_stamp_log[2 * i + 1];
+    }
+    dst[0] = base + n < 1024 ? base + n : 1024;
+  }
+}
+constexpr int kStaticSmemReserve = 2 * kMaxStamps * 8 + 128;
+#else
+__device__ __forceinline__ void stamp(int) {}
+__device__ __forceinline__ void stamp_begin(bool) {}
+__device__ __forceinline__ void stamp_flush(long long*) {}
+constexpr int kStaticSmemReserve = 128;
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Skinny product with a stationary weight slice (the recurrent / projection steps):
 //
 //   red[s*ldred + n] = sum_{k<K} X[s][k] * W[n][k]      s < Sg, n < Nc
 //
-// X is [Sg x K] in global memory (written by other CTAs before the preceding group barrier)
-// and is streamed through a double-buffered shared-memory ring with cp.async in K-chunks;
-// W is [Nc x K] resident in shared memory (row stride ldw).  Each thread owns a 4x4
-// (streams x columns) register tile; the K range of a chunk is split over `ksplit` adjacent
-// lanes whose partial sums are combined with warp shuffles (ksplit is a power of two <= 32).
-// All kThreads threads must call this (it contains __syncthreads and full-warp shuffles).
+// X is [Sg x K] in global memory (written by other CTAs before the preceding group barrier) and is
+// streamed through a ring of shared-memory slots of [Sg x kch] floats with cp.async; ALL chunks that fit
+// are put in flight at once so the L2 round trip is paid once per phase.  W is [Nc x K] resident in
+// shared memory (row stride ldw).  Each thread owns a 4x4 (streams x columns) register tile; the K
+// range of a chunk is split over `ksplit` adjacent lanes whose partial sums are combined with warp
+// shuffles (ksplit is a power of two <= 32).  The thread->tile mapping (a "plan") depends only on
+// (Sg, Nc, K) and is computed once per launch, outside the time loop.
+// All kThreads threads must call skinny_gemm (it contains __syncthreads and full-warp shuffles).
 // ---------------------------------------------------------------------------------------
-struct SkinnyMap {
-  int n_s_tiles, n_n_tiles, tiles, ksplit;
-  __device__ __forceinline__ void make(int Sg, int Nc) {
-    n_s_tiles = ceil_div(Sg, 4);
-    n_n_tiles = ceil_div(Nc, 4);
-    tiles = n_s_tiles * n_n_tiles;
-    int ks = kThreads / tiles;
-    ksplit = ks >= 1 ? pow2_floor(ks < 32 ? ks : 32) : 1;
-  }
+constexpr int kXbufPadMax = 16;
+__device__ __forceinline__ int xbuf_ld(int kch, int ksplit) { return kch + (ksplit < 8 ? 4 * ksplit : 4); }
+
+struct SkinnyPlan {          // lives in shared memory; uniform fields + one packed word per thread
+  int Sg, Nc, K;
+  int n_s_tiles, n_n_tiles, ksplit, npass;
+  int ts, tn, nbs, nblocks;  // a warp covers a ts x tn block of tiles; nbs blocks along s; nblocks total
+  int kch, nchunks, nslots, ldx, slot_floats;  // ring: slot_floats = Sg*ldx; panel: chunk c at column c*kch
+  int panel;                                   // 1: the whole [Sg x K] panel is resident (no slot reuse)
+  unsigned thr[kThreads];    // bit 31 active | kq [20,26) | n_tile [10,20) | s_tile [0,10)   (pass 0)
 };
 
-__device__ __forceinline__ int xbuf_ld(int KC, int ksplit) { return KC + (ksplit < 8 ? 4 * ksplit : 4); }
+// Tile coordinates of (warp-block wb, lane).  A warp holds 32/ksplit tiles arranged ts x tn so that the
+// distinct shared-memory rows touched by one LDS.128 stay few for BOTH operands (fewer wavefronts).
+__device__ __forceinline__ void skinny_tile_of(const SkinnyPlan* pl, int wb, int lane, bool* active, int* s_tile,
+                                               int* n_tile) {
+  const int t = lane / pl->ksplit;
+  const int ds = t % pl->ts, dn = t / pl->ts;
+  const int bs = wb % pl->nbs, bn = wb / pl->nbs;
+  *s_tile = bs * pl->ts + ds;
+  *n_tile = bn * pl->tn + dn;
+  *active = wb < pl->nblocks && *s_tile < pl->n_s_tiles && *n_tile < pl->n_n_tiles && pl->Nc > 0;
+  if (!*active) *s_tile = *n_tile = 0;
+}
 
-__device__ __forceinline__ void skinny_load_chunk(float* xs, int ldx, const float* __restrict__ Xg, size_t ldX,
-                                                  int Sg, int k0, int L) {
-  const int q_per_row = L >> 2;
-  const int total = Sg * q_per_row;
-  for (int idx = threadIdx.x; idx < total; idx += kThreads) {
-    int s = idx / q_per_row, q = idx - s * q_per_row;
-    cp_async16(xs + s * ldx + 4 * q, Xg + (size_t)s * ldX + k0 + 4 * q);
+// cap_floats: capacity of the shared all-gather buffer.  If the whole [Sg x K] panel fits, every chunk gets its
+// own columns and all of them are put in flight at once; otherwise a ring of [Sg x kch] slots is used.
+__device__ __forceinline__ void skinny_make_plan(SkinnyPlan* pl, int Sg, int Nc, int K, int cap_floats) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    const int n_s_tiles = ceil_div(Sg, 4), n_n_tiles = ceil_div(Nc > 0 ? Nc : 1, 4);
+    const int tiles = n_s_tiles * n_n_tiles;
+    int ks = kThreads / tiles;
+    const int ksplit = ks >= 1 ? pow2_floor(ks < 32 ? ks : 32) : 1;
+    const int tpw = 32 / ksplit;  // tiles per warp (power of two)
+    // ts x tn = tpw, as square as the tile grid allows
+    int ts = 1;
+    while (ts * ts < tpw) ts *= 2;             // ts = ceil-pow2(sqrt(tpw))
+    if (ts > tpw) ts = tpw;
+    while (ts > 1 && ts > pow2_floor(n_s_tiles) * 2) ts /= 2;
+    int tn = tpw / ts;
+    while (tn > 1 && tn > pow2_floor(n_n_tiles) * 2 && ts < tpw) { tn /= 2; ts *= 2; }
+    const int nbs = ceil_div(n_s_tiles, ts), nbn = ceil_div(n_n_tiles, tn);
+    pl->Sg = Sg; pl->Nc = Nc; pl->K = K;
+    pl->n_s_tiles = n_s_tiles; pl->n_n_tiles = n_n_tiles; pl->ksplit = ksplit;
+    pl->ts = ts; pl->tn = tn; pl->nbs = nbs; pl->nblocks = nbs * nbn;
+    pl->npass = ceil_div(nbs * nbn, kThreads / 32);
+    const int pad = (ksplit < 8 ? 4 * ksplit : 4);
+    const int kround = (K + 31) & ~31;
+    if ((long long)Sg * (kround + pad) <= cap_floats && Sg <= 16) {
+      int kch = kround;  // small stream groups: the whole K in one chunk, no per-chunk loop
+      while (ceil_div(K, kch) > 8) kch += 128;  // at most 8 cp.async groups in flight
+      pl->panel = 1; pl->kch = kch; pl->nchunks = ceil_div(K, kch); pl->nslots = pl->nchunks;
+      pl->ldx = kround + pad; pl->slot_floats = 0;
+    } else {
+      int kch = 256;
+      if ((long long)2 * Sg * (kch + pad) > cap_floats) kch = 128;
+      int ns = cap_floats / (Sg * (kch + pad));
+      pl->panel = 0; pl->kch = kch; pl->nchunks = ceil_div(K, kch); pl->nslots = ns > 8 ? 8 : (ns < 1 ? 1 : ns);
+      pl->ldx = kch + pad; pl->slot_floats = Sg * (kch + pad);
+    }
+  }
+  __syncthreads();
+  bool active;
+  int s_tile, n_tile;
+  skinny_tile_of(pl, tid >> 5, tid & 31, &active, &s_tile, &n_tile);
+  pl->thr[tid] = ((active ? 1u : 0u) << 31) | ((unsigned)((tid & 31) % pl->ksplit) << 20) | ((unsigned)n_tile << 10) |
+                 (unsigned)s_tile;
+}
+
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
   }
 }
 
-static __device__ __noinline__ void skinny_gemm(const float* __restrict__ Xg, size_t ldX, int K, int Sg,
-                                         const float* __restrict__ Ws, int ldw, int Nc, float* xbuf, int KC,
-                                         float* red, int ldred) {
-  SkinnyMap m;
-  m.make(Sg, Nc);
-  const int ldx = xbuf_ld(KC, m.ksplit);
-  const int tid = threadIdx.x;
-  const int pass_tiles = kThreads / m.ksplit;  // tiles processed concurrently
-  const int npass = ceil_div(m.tiles, pass_tiles);
-  const int kq = tid % m.ksplit;
-  const int nchunks = ceil_div(K, KC);
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ pl, const float* __restrict__ Xg,
+                                                size_t ldX, const float* __restrict__ Ws, int ldw, float* xbuf,
+                                                float* red, int ldred) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Sg = pl->Sg, Nc = pl->Nc, K = pl->K;
+  if (Nc <= 0) return;  // CTA-uniform
+  const int ksplit = pl->ksplit, ldx = pl->ldx, slot_floats = pl->slot_floats;
+  const int kch = pl->kch, nchunks = pl->nchunks, nslots = pl->nslots, npass = pl->npass;
+  const int n_s_tiles = pl->n_s_tiles, n_n_tiles = pl->n_n_tiles;
+  const bool panel = pl->panel != 0;
+  const unsigned packed = pl->thr[tid];
+  const int kq = (packed >> 20) & 63;
+
+  int issue_slot = 0, issue_k0 = 0;
+  auto issue = [&]() {  // next chunk -> its panel columns / the next ring slot
+    const int L = (K - issue_k0 < kch ? K - issue_k0 : kch) >> 2;  // 16-byte units per row
+    float* dst = panel ? xbuf + issue_k0 : xbuf + issue_slot * slot_floats;
+    const float* src = Xg + issue_k0;
+    for (int s = warp; s < Sg; s += kThreads / 32) {
+      float* d = dst + s * ldx;
+      const float* g = src + (size_t)s * ldX;
+      for (int u = lane; u < L; u += 32) cp_async16(d + 4 * u, g + 4 * u);
+    }
+    cp_async_commit();
+    issue_k0 += kch;
+    if (++issue_slot == nslots) issue_slot = 0;
+  };
 
   for (int pass = 0; pass < npass; ++pass) {
-    const int tile = pass * pass_tiles + tid / m.ksplit;
-    const bool active = tile < m.tiles;
-    const int s_tile = active ? tile % m.n_s_tiles : 0;
-    const int n_tile = active ? tile / m.n_s_tiles : 0;
-    int srow[4], ncol[4];
+    bool active;
+    int s_tile, n_tile;
+    if (pass == 0) {
+      active = (packed >> 31) != 0;
+      s_tile = packed & 1023;
+      n_tile = (packed >> 10) & 1023;
+    } else {
+      skinny_tile_of(pl, pass * (kThreads / 32) + warp, lane, &active, &s_tile, &n_tile);
+    }
+    // byte addresses (shared window) of this thread's 4 X rows and 4 W rows, at its first quad
+    uint32_t xa[4], wa[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int s = s_tile + i * m.n_s_tiles;
-      srow[i] = (s < Sg ? s : Sg - 1) * ldx;
-      int n = n_tile + i * m.n_n_tiles;
-      ncol[i] = (n < Nc ? n : Nc - 1) * ldw;
+      int s = s_tile + i * n_s_tiles;
+      xa[i] = smem_u32(xbuf) + (uint32_t)(((s < Sg ? s : Sg - 1) * ldx + 4 * kq) * 4);
+      int n = n_tile + i * n_n_tiles;
+      wa[i] = smem_u32(Ws) + (uint32_t)(((n < Nc ? n : Nc - 1) * ldw + 4 * kq) * 4);
     }
+    const uint32_t qstep = 16u * ksplit;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    skinny_load_chunk(xbuf, ldx, Xg, ldX, Sg, 0, (K < KC ? K : KC));
-    cp_async_commit();
+    issue_slot = 0;
+    issue_k0 = 0;
+    int issued = 0;
+    stamp(100);
+    for (; issued < nslots && issued < nchunks; ++issued) issue();
+    stamp(101);
+    int slot = 0;
     for (int c = 0; c < nchunks; ++c) {
-      const int k0 = c * KC;
-      const int L = (K - k0 < KC ? K - k0 : KC);
-      if (c + 1 < nchunks) {
-        const int k1 = k0 + KC;
-        skinny_load_chunk(xbuf + ((c + 1) & 1) * Sg * ldx, ldx, Xg, ldX, Sg, k1, (K - k1 < KC ? K - k1 : KC));
-        cp_async_commit();
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
+      cp_async_wait_dyn(issued - c - 1);
+      __syncthreads();  // chunk c landed for everyone; everyone is done with chunk c-1
+      stamp(110 + c);
+      if (c >= 1 && issued < nchunks) {
+        issue();  // ring only: into the slot chunk c-1 just vacated
+        ++issued;
       }
-      __syncthreads();
       if (active) {
-        const float* xs = xbuf + (c & 1) * Sg * ldx;
-        const float* ws = Ws + k0;
-        const int nq = L >> 2;
+        const int k0 = c * kch;
+        const int nq = (K - k0 < kch ? K - k0 : kch) >> 2;
+        const uint32_t xoff = (uint32_t)((panel ? k0 : slot * slot_floats) * 4), woff = (uint32_t)(k0 * 4);
+        // (a hand software-pipelined variant of this loop measured slower than letting ptxas schedule it)
+        uint32_t x0 = xa[0] + xoff, x1 = xa[1] + xoff, x2 = xa[2] + xoff, x3 = xa[3] + xoff;
+        uint32_t w0 = wa[0] + woff, w1 = wa[1] + woff, w2 = wa[2] + woff, w3 = wa[3] + woff;
 #pragma unroll 2
-        for (int q = kq; q < nq; q += m.ksplit) {
-          float4 xv[4], wv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + srow[i] + 4 * q);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4*>(ws + ncol[j] + 4 * q);
+        for (int q = kq; q < nq; q += ksplit) {
+          const float4 xv[4] = {lds128(x0), lds128(x1), lds128(x2), lds128(x3)};
+          const float4 wv[4] = {lds128(w0), lds128(w1), lds128(w2), lds128(w3)};
+          x0 += qstep; x1 += qstep; x2 += qstep; x3 += qstep;
+          w0 += qstep; w1 += qstep; w2 += qstep; w3 += qstep;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -235,10 +376,11 @@ static __device__ __noinline__ void skinny_gemm(const float* __restrict__ Xg, si
             }
         }
       }
-      __syncthreads();
+      if (++slot == nslots) slot = 0;
     }
+    stamp(130);
     // combine the ksplit partial sums held by adjacent lanes
-    for (int off = m.ksplit >> 1; off >= 1; off >>= 1) {
+    for (int off = ksplit >> 1; off >= 1; off >>= 1) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -247,18 +389,19 @@ static __device__ __noinline__ void skinny_gemm(const float* __restrict__ Xg, si
     if (active && kq == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        int s = s_tile + i * m.n_s_tiles;
+        int s = s_tile + i * n_s_tiles;
         if (s < Sg) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            int n = n_tile + j * m.n_n_tiles;
+            int n = n_tile + j * n_n_tiles;
             if (n < Nc) red[s * ldred + n] = acc[i][j];
           }
         }
       }
     }
+    __syncthreads();  // the all-gather buffer and red[] are safe to reuse
+    stamp(131);
   }
-  __syncthreads();
 }
 
 }  // namespace lstmp

@@ -66,6 +66,7 @@ struct lstmp_b200_engine {
   bool have_bwd = false; // a backpropagate record exists for T_last
   unsigned long long launches = 0;
   int gemm_backend = 0;
+  long long* dbg_stamps = nullptr;
   // optional per-kernel event timing
   bool timing = false;
   struct Ev { int kind; cudaEvent_t a, b; };
@@ -107,11 +108,13 @@ static bool make_decomp(int C, int R, int S, int sm_count, size_t smem_limit, in
   long long per = (long long)d.Sg * R;
   long long piece = (per + d.ctas_per_group - 1) / d.ctas_per_group;
   d.piece = (int)((piece + 3) & ~3LL);
-  d.KC = d.Sg <= 16 ? 128 : 64;
+  d.fwd_xcap = d.bwd_xcap = 0;
+  d.dbg = env_int("LSTMP_B200_DEBUG", 0);
   FwdParams f{};
   BwdParams b{};
-  size_t fsz = fwd_smem_floats(C, R, d, &f) * sizeof(float);
-  size_t bsz = bwd_smem_floats(C, R, d, &b) * sizeof(float);
+  const size_t limit_floats = (smem_limit - (size_t)static_smem_reserve()) / sizeof(float);  // static __shared__ + slack
+  size_t fsz = fwd_smem_floats(C, R, d, &f, limit_floats) * sizeof(float);
+  size_t bsz = bwd_smem_floats(C, R, d, &b, limit_floats) * sizeof(float);
   if (fsz > smem_limit || bsz > smem_limit) return false;
   *out = d;
   *fp = f;
@@ -141,6 +144,16 @@ extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
   for (float* b : bufs)
     if (b) cudaFree(b);
   if (h->bar) cudaFree(h->bar);
+  if (h->dbg_stamps) {
+    cudaDeviceSynchronize();
+    std::vector<long long> st(2 + 2 * 1024);
+    cudaMemcpy(st.data(), h->dbg_stamps, st.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long n = st[0];
+    fprintf(stderr, "[lstmp_b200 stamps] %lld records (tag: delta cycles from previous)\n", n);
+    for (long long i = 0; i < n && i < 1024; ++i)
+      fprintf(stderr, "  %4lld %8lld\n", st[2 + 2 * i], i ? st[3 + 2 * i] - st[1 + 2 * i] : 0LL);
+    cudaFree(h->dbg_stamps);
+  }
   delete h;
   return 0;
 }
@@ -229,8 +242,8 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     lstmp_b200_destroy(h);
     return rc;
   }
-  e = cudaMalloc((void**)&h->bar, kMaxGroupsHost * sizeof(unsigned));
-  if (e == cudaSuccess) e = cudaMemset(h->bar, 0, kMaxGroupsHost * sizeof(unsigned));
+  e = cudaMalloc((void**)&h->bar, (size_t)kMaxGroupsHost * kBarStride * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(h->bar, 0, (size_t)kMaxGroupsHost * kBarStride * sizeof(unsigned));
   if (e != cudaSuccess) {
     lstmp_b200_destroy(h);
     return fail((int)e, "barrier counters: %s", cudaGetErrorString(e));
@@ -240,6 +253,11 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
 #ifdef LSTMP_HAVE_TC_GEMM
   h->gemm_backend = env_int("LSTMP_B200_GEMM", 1) ? 1 : 0;
 #endif
+  if (h->d.dbg & 12) {
+    if (cudaMalloc((void**)&h->dbg_stamps, (2 + 2 * 1024) * sizeof(long long)) == cudaSuccess)
+      cudaMemset(h->dbg_stamps, 0, (2 + 2 * 1024) * sizeof(long long));
+    h->d.dbg_stamps = h->dbg_stamps;
+  }
   CUDA_TRY(cudaDeviceSynchronize());
   *out = h;
   return 0;

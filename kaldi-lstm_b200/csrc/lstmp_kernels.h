@@ -6,6 +6,7 @@
 namespace lstmp {
 
 constexpr int kMaxGroupsHost = 8;
+constexpr int kBarStride = 256;  // flags per group (>= CTAs per group), 1 KB apart
 
 // Work decomposition of one persistent launch (shared by forward and backward).
 //   grid = ngroups * ctas_per_group co-resident CTAs (cooperative launch, 1 CTA / SM).
@@ -14,14 +15,18 @@ constexpr int kMaxGroupsHost = 8;
 //     r columns  [j*rpc, j*rpc+rpc)      (rows of W_r_m for the projection, forward only)
 //     a `piece`-float slice of the group's flattened [Sg x R] d_r block (backward reduce-scatter).
 struct Decomp {
-  int ngroups, ctas_per_group, Sg, cpc, rpc, piece, KC;
+  int ngroups, ctas_per_group, Sg, cpc, rpc, piece;
+  int fwd_xcap, bwd_xcap;    // capacity (floats) of the shared-memory all-gather buffer
+  int dbg;                   // timing experiments only (LSTMP_B200_DEBUG): 1 = no group barrier, 2 = no products,
+                             // 4 = CTA 0 records clock64() stamps into dbg_stamps
+  long long* dbg_stamps;     // host-mapped [2 + 2*1024]: count, pad, then (tag, clock) pairs
 };
 
 struct FwdParams {
   int I, C, R, S, T;
   Decomp d;
   // dynamic shared memory carve-up (offsets in floats)
-  int off_wr, ldwr, off_wm, ldwm, off_xbuf, off_red, ldred, off_cprev, off_peep;
+  int off_wr, ldwr, off_wm, ldwm, off_xbuf, off_red, ldred, off_cprev, off_peep, off_plan;
   const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
   float *gifo;   // [T*S x 4C]  in: x*W_x^T + bias (pre-activations); out: g,i,f,o activations
   float *cbuf;   // [(T+1)*S x C]  block 0 = c_0
@@ -32,14 +37,14 @@ struct FwdParams {
   long long ld_out;
   float *state_c;  // [S x C]
   float *state_r;  // [S x R]
-  unsigned *bar;   // [ngroups]
+  unsigned *bar;   // [ngroups][kBarStride] per-CTA epoch flags
   unsigned bar_base[kMaxGroupsHost];
 };
 
 struct BwdParams {
   int I, C, R, S, T;
   Decomp d;
-  int off_wr, ldwr, off_wmt, ldwmt, off_xbuf, off_red, ldred, off_dgn, ldd, off_dcn, off_acc7, off_peep;
+  int off_wr, ldwr, off_wmt, ldwmt, off_xbuf, off_red, ldred, off_dgn, ldd, off_dcn, off_acc7, off_peep, off_plan;
   const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
   const float *gifo, *cbuf, *hbuf;
   const float *out_diff;
@@ -52,11 +57,12 @@ struct BwdParams {
   unsigned bar_base[kMaxGroupsHost];
 };
 
-size_t fwd_smem_floats(int C, int R, const Decomp& d, FwdParams* p);
-size_t bwd_smem_floats(int C, int R, const Decomp& d, BwdParams* p);
+size_t fwd_smem_floats(int C, int R, Decomp& d, FwdParams* p, size_t limit_floats);
+size_t bwd_smem_floats(int C, int R, Decomp& d, BwdParams* p, size_t limit_floats);
 cudaError_t launch_fwd(const FwdParams& p, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_bwd(const BwdParams& p, size_t smem_bytes, cudaStream_t stream);
 cudaError_t set_kernel_smem_limits(size_t fwd_bytes, size_t bwd_bytes);
+int static_smem_reserve();
 int fwd_barriers(int T);
 int bwd_barriers(int T);
 

@@ -31,7 +31,6 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_kernel(const __grid_con
   const int nc = max(0, min(p.d.cpc, C - c0));  // my cells
   const int r0 = j * p.d.rpc;
   const int nr = max(0, min(p.d.rpc, R - r0));  // my projection outputs
-  const int KC = p.d.KC;
 
   float* wr = smem + p.off_wr;      // [4*nc][ldwr]   rows: gate*nc + cl  (gate order g,i,f,o: LPS.h:234-243)
   float* wm = smem + p.off_wm;      // [nr][ldwm]
@@ -39,6 +38,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_kernel(const __grid_con
   float* red = smem + p.off_red;    // [Sg][ldred]
   float* cprev = smem + p.off_cprev;  // [Sg*nc]  c_{t-1} of my cells
   float* peep = smem + p.off_peep;    // [3][cpc]
+  SkinnyPlan* plan_g = reinterpret_cast<SkinnyPlan*>(smem + p.off_plan);  // gates:      [Sg x R] * [4nc x R]^T
+  SkinnyPlan* plan_p = plan_g + 1;                                         // projection: [Sg x C] * [nr x C]^T
+  skinny_make_plan(plan_g, Sg, 4 * nc, R, p.d.fwd_xcap);
+  skinny_make_plan(plan_p, Sg, nr, C, p.d.fwd_xcap);
 
   // ---- stage the stationary weight slices with TMA bulk copies (once per chunk) -----------
   if (tid == 0) {
@@ -78,9 +81,13 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_kernel(const __grid_con
   __syncthreads();
 
   GroupBarrier gb;
-  gb.init(p.bar + grp, p.bar_base[grp], (unsigned)p.d.ctas_per_group);
+  gb.init(p.bar + grp * kBarStride, p.bar_base[grp], (unsigned)p.d.ctas_per_group, (p.d.dbg & 1) != 0);
+  stamp_begin((p.d.dbg & 4) && blockIdx.x == 0);
+  __syncthreads();
+  stamp(1);
 
   for (int tt = 0; tt < T; ++tt) {
+    stamp(10);
     // ================= phase 1: gates + cell update for my cells ==========================
     if (nc > 0) {
       // prefetch this thread's first element's x-part pre-activations (input GEMM + bias)
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_kernel(const __grid_con
       // r_{t-1}: carried state for the first frame of the chunk, else rbuf block tt
       const float* X = (tt == 0) ? p.state_r + (size_t)s_base * R : p.rbuf + ((size_t)tt * S + s_base) * R;
       // gifo(t) += r(t-1) * W_gifo_r^T                                       (LPS.h:275)
-      skinny_gemm(X, (size_t)R, R, Sg, wr, p.ldwr, 4 * nc, xbuf, KC, red, p.ldred);
+      if (!(p.d.dbg & 2)) skinny_gemm(plan_g, X, (size_t)R, wr, p.ldwr, xbuf, red, p.ldred);
       for (int idx = tid; idx < Sg * nc; idx += kThreads) {
         int s = idx / nc, cl = idx - s * nc;
         size_t row = (size_t)tt * S + s_base + s;
@@ -131,11 +138,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_kernel(const __grid_con
         cprev[idx] = c;
       }
     }
+    stamp(20);
     gb.sync();
+    stamp(21);
     // ================= phase 2: projection r(t) = m(t) * W_r_m^T for my columns (LPS.h:312) ==
     if (nr > 0) {
-      skinny_gemm(p.mbuf + ((size_t)tt * S + s_base) * C, (size_t)C, C, Sg, wm, p.ldwm, nr, xbuf, KC, red,
-                  p.ldred);
+      if (!(p.d.dbg & 2)) skinny_gemm(plan_p, p.mbuf + ((size_t)tt * S + s_base) * C, (size_t)C, wm, p.ldwm, xbuf, red, p.ldred);
       for (int idx = tid; idx < Sg * nr; idx += kThreads) {
         int s = idx / nr, n = idx - s * nr;
         float v = red[s * p.ldred + n];
@@ -145,18 +153,32 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_kernel(const __grid_con
         if (tt == T - 1) p.state_r[(size_t)(s_base + s) * R + r0 + n] = v;   // :331
       }
     }
+    stamp(30);
     if (tt + 1 < T) gb.sync();
+    stamp(31);
   }
   // prev_nnet_state_ <- last frame (LPS.h:331): c part
   for (int idx = tid; idx < Sg * nc; idx += kThreads) {
     int s = idx / nc, cl = idx - s * nc;
     p.state_c[(size_t)(s_base + s) * C + c0 + cl] = cprev[idx];
   }
+  stamp_flush(p.d.dbg_stamps);
 }
 
-int fwd_barriers(int T) { return 2 * T - 1; }
+int fwd_barriers(int T) { return 2 * T - 1; }  // barrier epochs consumed by one launch
 
-size_t fwd_smem_floats(int C, int R, const Decomp& d, FwdParams* p) {
+// The all-gather buffer takes whatever shared memory is left beside the weights; it must hold at least
+// two [Sg x 128] ring slots.  The device-side plan decides between a resident panel and a ring.
+static bool xbuf_capacity(size_t used_floats, size_t limit_floats, int Sg, int* cap) {
+  const size_t avail = limit_floats > used_floats ? limit_floats - used_floats : 0;
+  if (avail < (size_t)2 * Sg * (128 + kXbufPadMax)) return false;
+  *cap = (int)(avail & ~size_t(3));
+  return true;
+}
+
+int static_smem_reserve() { return kStaticSmemReserve; }
+
+size_t fwd_smem_floats(int C, int R, Decomp& d, FwdParams* p, size_t limit_floats) {
   size_t off = 0;
   auto take = [&](size_t n) {
     size_t o = off;
@@ -167,12 +189,19 @@ size_t fwd_smem_floats(int C, int R, const Decomp& d, FwdParams* p) {
   p->off_wr = take((size_t)4 * d.cpc * p->ldwr);
   p->ldwm = C + 4;
   p->off_wm = take((size_t)d.rpc * p->ldwm);
-  p->off_xbuf = take((size_t)2 * d.Sg * (d.KC + 16));
   int ldred = 4 * d.cpc > d.rpc ? 4 * d.cpc : d.rpc;
   p->ldred = ldred | 1;
   p->off_red = take((size_t)d.Sg * p->ldred);
   p->off_cprev = take((size_t)d.Sg * d.cpc);
   p->off_peep = take((size_t)3 * d.cpc);
+  p->off_plan = take(2 * (sizeof(SkinnyPlan) / sizeof(float)) + 4);
+  if (!xbuf_capacity(off + 16, limit_floats, d.Sg, &d.fwd_xcap)) return (size_t)1 << 40;
+  // no need for more than the largest full panel
+  size_t want = (size_t)d.Sg * ((((C > R ? C : R) + 31) & ~31) + kXbufPadMax);
+  const size_t ring_min = (size_t)2 * d.Sg * (128 + kXbufPadMax);  // what the device-side ring plan assumes
+  if (want < ring_min) want = ring_min;
+  if ((size_t)d.fwd_xcap > want) d.fwd_xcap = (int)want;
+  p->off_xbuf = take((size_t)d.fwd_xcap);
   return off;
 }
 
@@ -234,7 +263,6 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_kernel(const __grid_con
   const int s_base = grp * Sg;
   const int c0 = j * p.d.cpc;
   const int nc = max(0, min(p.d.cpc, C - c0));
-  const int KC = p.d.KC;
   const int nper = Sg * R;  // floats in the group's d_r block
   const int e0 = min(nper, j * p.d.piece);
   const int e1 = min(nper, e0 + p.d.piece);  // my reduce-scatter slice [e0,e1)
@@ -247,6 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_kernel(const __grid_con
   float* dcn = smem + p.off_dcn;    // [Sg*nc]      d_c(t+1)
   float* acc7 = smem + p.off_acc7;  // [Sg*nc][7]   running sums for bias / peephole gradients
   float* peep = smem + p.off_peep;
+  SkinnyPlan* plan_m = reinterpret_cast<SkinnyPlan*>(smem + p.off_plan);  // d_m: [Sg x R] * [nc x R]^T
+  skinny_make_plan(plan_m, Sg, nc, R, p.d.bwd_xcap);
 
   if (tid == 0) {
     mbar_init(&mbar, 1);
@@ -277,7 +307,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_kernel(const __grid_con
   __syncthreads();
 
   GroupBarrier gb;
-  gb.init(p.bar + grp, p.bar_base[grp], (unsigned)p.d.ctas_per_group);
+  gb.init(p.bar + grp * kBarStride, p.bar_base[grp], (unsigned)p.d.ctas_per_group, (p.d.dbg & 1) != 0);
+  stamp_begin((p.d.dbg & 8) && blockIdx.x == 0);
+  __syncthreads();
+  stamp(2);
   float* my_scratch = p.scratch + ((size_t)grp * p.d.ctas_per_group + j) * nper;
   const float* grp_scratch = p.scratch + (size_t)grp * p.d.ctas_per_group * nper;
   // number of CTAs of the group that own cells (the only ones that write partials)
@@ -286,9 +319,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_kernel(const __grid_con
   for (int tt = T - 1; tt >= 0; --tt) {
     const bool have_next = (tt + 1 < T);
     // ============ phase A: partial d_r(t) = DGIFO(t+1)[:, my rows] * W_gifo_r[my rows, :]   (:391)
+    stamp(40);
     if (have_next) {
-      if (nc > 0) outer_gemm(dgn, p.ldd, wr, p.ldwr, 4 * nc, Sg, R, my_scratch);
+      if (nc > 0 && !(p.d.dbg & 2)) outer_gemm(dgn, p.ldd, wr, p.ldwr, 4 * nc, Sg, R, my_scratch);
+      stamp(41);
       gb.sync();
+      stamp(42);
     }
     // ============ phase A2: reduce-scatter.  d_r(t)[e0:e1) = out_diff(t) + sum of partials    (:367,:391)
     {
@@ -328,20 +364,35 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_kernel(const __grid_con
       }
       (void)ncw;
     }
+    stamp(43);
     gb.sync();
+    stamp(44);
     // ============ phase B: d_m = d_r * W_r_m (my cells) (:408) + gate derivatives (:411-440)
     if (nc > 0) {
-      skinny_gemm(p.dr + ((size_t)tt * S + s_base) * R, (size_t)R, R, Sg, wmt, p.ldwmt, nc, xbuf, KC, red,
-                  p.ldred);
+      // prefetch this thread's first element's activations while d_r is gathered and contracted
+      float yg = 0.f, yi = 0.f, yf = 0.f, yo = 0.f, yc = 0.f, ycp = 0.f, yh = 0.f, yfn = 0.f;
+      if (tid < Sg * nc) {
+        int s = tid / nc, cl = tid - s * nc;
+        size_t row = (size_t)tt * S + s_base + s;
+        const float* gp = p.gifo + row * (4 * C) + c0 + cl;
+        yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
+        yc = p.cbuf[(row + S) * C + c0 + cl];
+        ycp = p.cbuf[row * C + c0 + cl];
+        yh = p.hbuf[row * C + c0 + cl];
+        yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;
+      }
+      if (!(p.d.dbg & 2)) skinny_gemm(plan_m, p.dr + ((size_t)tt * S + s_base) * R, (size_t)R, wmt, p.ldwmt, xbuf, red, p.ldred);
       for (int idx = tid; idx < Sg * nc; idx += kThreads) {
         int s = idx / nc, cl = idx - s * nc;
         size_t row = (size_t)tt * S + s_base + s;
-        const float* gp = p.gifo + row * (4 * C) + c0 + cl;
-        float yg = gp[0], yi = gp[C], yf = gp[2 * C], yo = gp[3 * C];
-        float yc = p.cbuf[(row + S) * C + c0 + cl];
-        float ycp = p.cbuf[row * C + c0 + cl];  // c(t-1): block tt
-        float yh = p.hbuf[row * C + c0 + cl];
-        float yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;  // f(t+1)
+        if (idx >= kThreads) {
+          const float* gp = p.gifo + row * (4 * C) + c0 + cl;
+          yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
+          yc = p.cbuf[(row + S) * C + c0 + cl];
+          ycp = p.cbuf[row * C + c0 + cl];  // c(t-1): block tt
+          yh = p.hbuf[row * C + c0 + cl];
+          yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;  // f(t+1)
+        }
         float pi = peep[cl], pf = peep[p.d.cpc + cl], po = peep[2 * p.d.cpc + cl];
         float d_m = red[s * p.ldred + cl];
         float d_h = (d_m * yo) * (1.0f - yh * yh);            // :411-412
@@ -374,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_kernel(const __grid_con
         a7[6] += d_o * yc;     // peephole_o_c_corr_  DO(t) .* C(t)    (:483)
       }
       __syncthreads();  // dgn complete before phase A of the next (earlier) frame reads it
+      stamp(45);
     }
   }
   // per-group partial bias / peephole gradients: sum my cells over my streams (fixed order)
@@ -385,11 +437,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_kernel(const __grid_con
     for (int s = 0; s < Sg; ++s) a += acc7[(size_t)(s * nc + cl) * 7 + w];
     sg[(size_t)w * C + c0 + cl] = a;
   }
+  stamp_flush(p.d.dbg_stamps);
 }
 
 int bwd_barriers(int T) { return 2 * T - 1; }
 
-size_t bwd_smem_floats(int C, int R, const Decomp& d, BwdParams* p) {
+size_t bwd_smem_floats(int C, int R, Decomp& d, BwdParams* p, size_t limit_floats) {
   size_t off = 0;
   auto take = [&](size_t n) {
     size_t o = off;
@@ -401,9 +454,6 @@ size_t bwd_smem_floats(int C, int R, const Decomp& d, BwdParams* p) {
   p->off_wr = take((size_t)4 * d.cpc * p->ldwr);
   p->ldwmt = R + 4;
   p->off_wmt = take((size_t)d.cpc * p->ldwmt);
-  size_t xb = (size_t)2 * d.Sg * (d.KC + 16);
-  if (xb < (size_t)4 * kThreads) xb = (size_t)4 * kThreads;  // also the reduce-scatter exchange buffer
-  p->off_xbuf = take(xb);
   p->ldred = d.cpc | 1;
   p->off_red = take((size_t)d.Sg * p->ldred);
   p->ldd = (d.Sg + 7) & ~7;
@@ -411,6 +461,15 @@ size_t bwd_smem_floats(int C, int R, const Decomp& d, BwdParams* p) {
   p->off_dcn = take((size_t)d.Sg * d.cpc);
   p->off_acc7 = take((size_t)d.Sg * d.cpc * 7);
   p->off_peep = take((size_t)3 * d.cpc);
+  p->off_plan = take((sizeof(SkinnyPlan) / sizeof(float)) + 4);
+  if (!xbuf_capacity(off + 16 + 4 * kThreads, limit_floats, d.Sg, &d.bwd_xcap)) return (size_t)1 << 40;
+  size_t want = (size_t)d.Sg * (((R + 31) & ~31) + kXbufPadMax);
+  const size_t ring_min = (size_t)2 * d.Sg * (128 + kXbufPadMax);
+  if (want < ring_min) want = ring_min;
+  if ((size_t)d.bwd_xcap > want) d.bwd_xcap = (int)want;
+  size_t xb = (size_t)d.bwd_xcap;
+  if (xb < (size_t)4 * kThreads) xb = (size_t)4 * kThreads;  // also the reduce-scatter exchange buffer
+  p->off_xbuf = take(xb);
   return off;
 }
 

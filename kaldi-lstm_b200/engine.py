@@ -44,7 +44,8 @@ class Timing(ctypes.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "_lib", "liblstmp_b200.so")
+    # LSTMP_B200_LIB selects an alternative build of the same library (e.g. the clock-stamp build)
+    return os.environ.get("LSTMP_B200_LIB") or os.path.join(_HERE, "_lib", "liblstmp_b200.so")
 
 
 def load_library():
