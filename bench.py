@@ -253,7 +253,7 @@ def main():
             d = in_diffs[li]
         if world > 1:                                         # one sum all-reduce of the fresh gradients per Update
             for gv in grad_views:
-                dist.all_reduce(gv, op=dist.ReduceOp.SUM)
+                dist.all_reduce(gv, op=dist.ReduceOp.SUM)     # == klb.parallel.allreduce_gradients(layers)
         for comp in layers:
             comp.Update()
 

@@ -13,3 +13,4 @@ library or without a B200 raises.
 from .engine import Engine, EngineError, lib_path, load_library  # noqa: F401
 from .component import LstmProjectedStreams, NnetTrainOptions  # noqa: F401
 from .dispatch import StreamDispatcher  # noqa: F401
+from . import parallel  # noqa: F401

@@ -176,6 +176,10 @@ class LstmProjectedStreams:
         self.BackpropagateFnc(in_, out, out_diff, in_diff)
         return in_diff
 
+    def fresh_gradient(self):
+        """Zero-copy tensor view of the fresh-gradient arena (what a data-parallel caller all-reduces)."""
+        return self._engine.arena_tensor(2)
+
     @property
     def engine(self):
         return self._engine

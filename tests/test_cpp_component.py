@@ -1,0 +1,33 @@
+"""The C++ host-side mirror of the reference component (kaldi-lstm_b200/kaldi/b200-lstm-projected-streams.h,
+built against the compat Kaldi surface) exercised through its own test driver (tests/cpp/component_test.cc)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "_build", "component_test")
+ORACLE = os.path.join(ROOT, "oracle", "_build", "liblstmp_oracle.so")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+
+
+def test_cpp_component_builds_and_fails_loudly_without_gpu():
+    _build()
+    assert os.path.exists(BIN)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([BIN, ORACLE], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+@pytest.mark.gpu
+def test_cpp_component_parity_on_gpu():
+    _build()
+    r = subprocess.run([BIN, ORACLE], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
