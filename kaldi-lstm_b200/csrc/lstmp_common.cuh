@@ -277,6 +277,22 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
   }
 }
 
+// Packed 2-wide FP32 FMA (Blackwell FFMA2, PTX fma.rn.f32x2): two fp32 FMAs per issued instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -331,11 +347,13 @@ static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ p
       wa[i] = smem_u32(Ws) + (uint32_t)(((n < Nc ? n : Nc - 1) * ldw + 4 * kq) * 4);
     }
     const uint32_t qstep = 16u * ksplit;
-    float acc[4][4];
+    // acc2[i][j] = (sum over even k, sum over odd k) of X[s_i][k] * W[n_j][k]: the natural (x,y) / (z,w) register
+    // pairs of the 128-bit loads feed FFMA2 directly, no operand duplication.
+    f32x2 acc2[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
 
     issue_slot = 0;
     issue_k0 = 0;
@@ -365,20 +383,35 @@ static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ p
           const float4 wv[4] = {lds128(w0), lds128(w1), lds128(w2), lds128(w3)};
           x0 += qstep; x1 += qstep; x2 += qstep; x3 += qstep;
           w0 += qstep; w1 += qstep; w2 += qstep; w3 += qstep;
+          f32x2 xl[4], xh[4], wl[4], wh[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            xl[i] = pack2(xv[i].x, xv[i].y);
+            xh[i] = pack2(xv[i].z, xv[i].w);
+            wl[i] = pack2(wv[i].x, wv[i].y);
+            wh[i] = pack2(wv[i].z, wv[i].w);
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              acc[i][j] = fmaf(xv[i].x, wv[j].x, acc[i][j]);
-              acc[i][j] = fmaf(xv[i].y, wv[j].y, acc[i][j]);
-              acc[i][j] = fmaf(xv[i].z, wv[j].z, acc[i][j]);
-              acc[i][j] = fmaf(xv[i].w, wv[j].w, acc[i][j]);
+              acc2[i][j] = ffma2(xl[i], wl[j], acc2[i][j]);
+              acc2[i][j] = ffma2(xh[i], wh[j], acc2[i][j]);
             }
         }
       }
       if (++slot == nslots) slot = 0;
     }
     stamp(130);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float e, o;
+        unpack2(acc2[i][j], e, o);
+        acc[i][j] = e + o;
+      }
     // combine the ksplit partial sums held by adjacent lanes
     for (int off = ksplit >> 1; off >= 1; off >>= 1) {
 #pragma unroll

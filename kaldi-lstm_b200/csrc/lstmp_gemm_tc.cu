@@ -85,6 +85,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Global operand load that the compiler may not sink towards its use: the point of the two register sets is
+// that these loads are ISSUED two K blocks ahead (ncu showed stall_long_sb on the first use otherwise).
+__device__ __forceinline__ float4 ldg_early(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
 // One operand's loader state.  The shared-memory tile is ALWAYS K-major (the layout validated on
 // hardware); a source stored with the M/N index contiguous ("MN-major", e.g. DGIFO^T for the weight
 // gradients) is transposed on the fly in registers: each thread owns a 4(k) x 4(mn) block, loads it with
@@ -105,7 +115,7 @@ struct Loader {
         const int kc = u % (BK / 4), r = u / (BK / 4);
         const int gr = row0 + r, gk = k0 + 4 * kc;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < nrows && gk < K) x = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gk));
+        if (gr < nrows && gk < K) x = ldg_early(src + (size_t)gr * ld + gk);
         v[i] = x;
       }
     } else {
@@ -119,7 +129,7 @@ struct Loader {
         for (int kk = 0; kk < 4; ++kk) {
           const int gk = k0 + 4 * kc + kk;
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (b < NBLK && gr < nrows && gk < K) x = __ldg(reinterpret_cast<const float4*>(src + (size_t)gk * ld + gr));
+          if (b < NBLK && gr < nrows && gk < K) x = ldg_early(src + (size_t)gk * ld + gr);
           v[blk * 4 + kk] = x;  // row kk of the block: 4 consecutive mn at k = 4kc+kk
         }
       }

@@ -224,9 +224,13 @@ __device__ __forceinline__ void outer_gemm(const float* __restrict__ dT, int ldd
   const int tiles = nkq * nst;
   for (int tile = threadIdx.x; tile < tiles; tile += kThreads) {
     const int kq = tile % nkq, st = tile / nkq;
-    float4 acc[8];
+    // acc2[p][c] = (P[2p][c], P[2p+1][c]): stream pairs come straight from the 128-bit loads of dT, the weight
+    // component is duplicated once per n (4 packs per 16 FFMA2).
+    f32x2 acc2[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int pq = 0; pq < 4; ++pq)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc2[pq][c] = 0ull;
     const float* wp = Ws + 4 * kq;
     const float* dp = dT + 8 * st;
 #pragma unroll 2
@@ -234,14 +238,20 @@ __device__ __forceinline__ void outer_gemm(const float* __restrict__ dT, int ldd
       float4 w = *reinterpret_cast<const float4*>(wp + (size_t)n * ldw);
       float4 d0 = *reinterpret_cast<const float4*>(dp + (size_t)n * ldd);
       float4 d1 = *reinterpret_cast<const float4*>(dp + (size_t)n * ldd + 4);
-      float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      const f32x2 dv[4] = {pack2(d0.x, d0.y), pack2(d0.z, d0.w), pack2(d1.x, d1.y), pack2(d1.z, d1.w)};
+      const f32x2 wv[4] = {pack2(w.x, w.x), pack2(w.y, w.y), pack2(w.z, w.z), pack2(w.w, w.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i].x = fmaf(dv[i], w.x, acc[i].x);
-        acc[i].y = fmaf(dv[i], w.y, acc[i].y);
-        acc[i].z = fmaf(dv[i], w.z, acc[i].z);
-        acc[i].w = fmaf(dv[i], w.w, acc[i].w);
-      }
+      for (int pq = 0; pq < 4; ++pq)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc2[pq][c] = ffma2(dv[pq], wv[c], acc2[pq][c]);
+    }
+    float4 acc[8];
+#pragma unroll
+    for (int pq = 0; pq < 4; ++pq) {
+      unpack2(acc2[pq][0], acc[2 * pq].x, acc[2 * pq + 1].x);
+      unpack2(acc2[pq][1], acc[2 * pq].y, acc[2 * pq + 1].y);
+      unpack2(acc2[pq][2], acc[2 * pq].z, acc[2 * pq + 1].z);
+      unpack2(acc2[pq][3], acc[2 * pq].w, acc[2 * pq + 1].w);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
