@@ -61,7 +61,9 @@ const char* lstmp_b200_last_error(void);
  * (<NumStream>), max_frames = largest T (BPTT chunk length) a later call will use.
  * Requires I % 4 == 0, C % 4 == 0, R % 4 == 0 (128-bit vector / TMA bulk granularity).
  * Parameters start at zero; gradient/momentum buffers and the carried state start at zero
- * (LPS.h:76,89-97). */
+ * (LPS.h:76,89-97).  When the layer's weight slices fit in shared memory across the SMs (800/512 does) the
+ * persistent per-chunk kernels are used; otherwise (e.g. 2048/1024) the engine falls back to a weights-streamed
+ * per-timestep CUDA path with the same results (lstmp_b200_info_t.weights_streamed). */
 int lstmp_b200_create(int input_dim, int cell_dim, int recur_dim, int num_stream, int max_frames, int device,
                       lstmp_b200_handle_t* out);
 int lstmp_b200_destroy(lstmp_b200_handle_t h);
@@ -128,6 +130,7 @@ typedef struct {
   size_t workspace_bytes;          /* activations + scratch owned by the engine */
   unsigned long long kernel_launches; /* kernels launched by this handle so far */
   int gemm_backend;                /* 0 = fp32 SIMT, 1 = tcgen05 3xTF32 */
+  int weights_streamed;            /* 1: weight slices do not fit in shared memory; per-timestep GEMM path */
 } lstmp_b200_info_t;
 int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* info);
 

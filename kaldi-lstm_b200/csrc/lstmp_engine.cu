@@ -67,6 +67,9 @@ struct lstmp_b200_engine {
   unsigned long long launches = 0;
   int gemm_backend = 0;
   long long* dbg_stamps = nullptr;
+  // weights-streamed mode: slices do not fit in shared memory -> per-step GEMMs + elementwise kernels
+  bool streamed = false;
+  float *dm = nullptr, *dc2 = nullptr;
   // optional per-kernel event timing
   bool timing = false;
   struct Ev { int kind; cudaEvent_t a, b; };
@@ -140,7 +143,7 @@ extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   float* bufs[] = {h->params, h->corr, h->grads, h->state_c, h->state_r, h->gifo, h->cbuf, h->hbuf,
-                   h->mbuf,   h->rbuf, h->dgifo, h->dr,      h->scratch, h->small_grads};
+                   h->mbuf,   h->rbuf, h->dgifo, h->dr,      h->scratch, h->small_grads, h->dm, h->dc2};
   for (float* b : bufs)
     if (b) cudaFree(b);
   if (h->bar) cudaFree(h->bar);
@@ -205,17 +208,21 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
       ok = make_decomp(C, R, S, sm_use, smem_limit, g, &h->d, &h->fp, &h->bp, &h->fwd_smem, &h->bwd_smem);
     }
   }
+  if (env_int("LSTMP_B200_FORCE_STREAMED", 0)) ok = false;
   if (!ok) {
-    delete h;
-    return fail(LSTMP_B200_ENOMEM,
-                "weight slices of a %d-cell/%d-proj layer do not fit in %zu B of shared memory per SM over %d SMs "
-                "(weights-streamed mode not built yet)",
-                C, R, smem_limit, sm_use);
-  }
-  e = set_kernel_smem_limits(h->fwd_smem, h->bwd_smem);
-  if (e != cudaSuccess) {
-    delete h;
-    return fail((int)e, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e));
+    // The slices of this layer do not fit in shared memory across the SMs (e.g. 2048-cell/1024-proj): fall back
+    // to the weights-streamed per-timestep path (still CUDA only).
+    h->streamed = true;
+    h->d = Decomp{};
+    h->d.ngroups = 1;
+    h->d.ctas_per_group = sm_use;
+    h->d.Sg = S;
+  } else {
+    e = set_kernel_smem_limits(h->fwd_smem, h->bwd_smem);
+    if (e != cudaSuccess) {
+      delete h;
+      return fail((int)e, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e));
+    }
   }
 
   // arenas
@@ -237,7 +244,9 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
       (rc = alloc_f(&h->cbuf, TS1 * C, &ws)) || (rc = alloc_f(&h->hbuf, TS * C, &ws)) ||
       (rc = alloc_f(&h->mbuf, TS * C, &ws)) || (rc = alloc_f(&h->rbuf, TS1 * R, &ws)) ||
       (rc = alloc_f(&h->dgifo, TS * 4 * C, &ws)) || (rc = alloc_f(&h->dr, TS * R, &ws)) ||
-      (rc = alloc_f(&h->scratch, (size_t)h->d.ngroups * h->d.ctas_per_group * h->d.Sg * R, &ws)) ||
+      (rc = alloc_f(&h->scratch, h->streamed ? 4 : (size_t)h->d.ngroups * h->d.ctas_per_group * h->d.Sg * R, &ws)) ||
+      (rc = alloc_f(&h->dm, h->streamed ? (size_t)S * C : 4, &ws)) ||
+      (rc = alloc_f(&h->dc2, h->streamed ? (size_t)2 * S * C : 4, &ws)) ||
       (rc = alloc_f(&h->small_grads, (size_t)h->d.ngroups * 7 * C, &ws))) {
     lstmp_b200_destroy(h);
     return rc;
@@ -439,6 +448,38 @@ extern "C" int lstmp_b200_propagate(lstmp_b200_handle_t h, const float* in, size
   if ((rc = gemm(h, 0, h->gifo, 4 * C, num_rows, 4 * C, I, 1.f, in, (long long)ld_in, 0, h->params + h->off_wx, I, 1,
                  0.f, h->params + h->off_bias, st)))
     return rc;
+  if (h->streamed) {
+    const float* W = h->params;
+    CUDA_TRY(cudaMemcpyAsync(h->cbuf, h->state_c, (size_t)S * C * sizeof(float), cudaMemcpyDeviceToDevice, st));  // :231
+    CUDA_TRY(cudaMemcpyAsync(h->rbuf, h->state_r, (size_t)S * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int t = 0; t < T; ++t) {
+      float* gifo_t = h->gifo + (size_t)t * S * 4 * C;
+      // gifo(t) += r(t-1) * W_gifo_r^T                                       (LPS.h:275)
+      if ((rc = gemm(h, 1, gifo_t, 4 * C, S, 4 * C, R, 1.f, h->rbuf + (size_t)t * S * R, R, 0, W + h->off_wr, R, 1, 1.f,
+                     nullptr, st)))
+        return rc;
+      {
+        Timed tm(h, 1, st);
+        CUDA_TRY(launch_streamed_fwd_elem(gifo_t, h->cbuf + (size_t)t * S * C, h->cbuf + (size_t)(t + 1) * S * C,
+                                          h->hbuf + (size_t)t * S * C, h->mbuf + (size_t)t * S * C, W + h->off_pi,
+                                          W + h->off_pf, W + h->off_po, S, C, st));
+      }
+      h->launches++;
+      // r(t) = m(t) * W_r_m^T                                                  (LPS.h:312)
+      if ((rc = gemm(h, 1, h->rbuf + (size_t)(t + 1) * S * R, R, S, R, C, 1.f, h->mbuf + (size_t)t * S * C, C, 0,
+                     W + h->off_wm, C, 1, 0.f, nullptr, st)))
+        return rc;
+    }
+    CUDA_TRY(cudaMemcpy2DAsync(out, ld_out * sizeof(float), h->rbuf + (size_t)S * R, R * sizeof(float), R * sizeof(float),
+                               (size_t)num_rows, cudaMemcpyDeviceToDevice, st));                                  // :328
+    CUDA_TRY(cudaMemcpyAsync(h->state_c, h->cbuf + (size_t)T * S * C, (size_t)S * C * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));                                                       // :331
+    CUDA_TRY(cudaMemcpyAsync(h->state_r, h->rbuf + (size_t)T * S * R, (size_t)S * R * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+    h->T_last = T;
+    h->have_bwd = false;
+    return 0;
+  }
   FwdParams p = h->fp;
   p.I = I; p.C = C; p.R = R; p.S = S; p.T = T;
   p.d = h->d;
@@ -476,6 +517,40 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
     return fail(LSTMP_B200_EINVAL, "stride < columns");
   cudaStream_t st = (cudaStream_t)stream;
   const int C = h->C, R = h->R, I = h->I, S = h->S, T = h->T_last;
+  int rc;
+  if (h->streamed) {
+    const float* W = h->params;
+    CUDA_TRY(cudaMemcpy2DAsync(h->dr, R * sizeof(float), out_diff, ld_od * sizeof(float), R * sizeof(float),
+                               (size_t)num_rows, cudaMemcpyDeviceToDevice, st));                                  // :367
+    for (int t = T - 1; t >= 0; --t) {
+      const bool next = t + 1 < T;
+      float* dr_t = h->dr + (size_t)t * S * R;
+      // d_r(t) += DGIFO(t+1) * w_gifo_r                                        (LPS.h:391)
+      if (next && (rc = gemm(h, 2, dr_t, R, S, R, 4 * C, 1.f, h->dgifo + (size_t)(t + 1) * S * 4 * C, 4 * C, 0,
+                             W + h->off_wr, R, 0, 1.f, nullptr, st)))
+        return rc;
+      // d_m = d_r * w_r_m                                                       (LPS.h:408)
+      if ((rc = gemm(h, 2, h->dm, C, S, C, R, 1.f, dr_t, R, 0, W + h->off_wm, C, 0, 0.f, nullptr, st))) return rc;
+      float* dc_t = h->dc2 + (size_t)(t & 1) * S * C;
+      const float* dc_n = h->dc2 + (size_t)((t + 1) & 1) * S * C;
+      {
+        Timed tm(h, 2, st);
+        CUDA_TRY(launch_streamed_bwd_elem(h->dm, h->gifo + (size_t)t * S * 4 * C,
+                                          next ? h->gifo + (size_t)(t + 1) * S * 4 * C : nullptr,
+                                          h->cbuf + (size_t)(t + 1) * S * C, h->cbuf + (size_t)t * S * C,
+                                          h->hbuf + (size_t)t * S * C,
+                                          next ? h->dgifo + (size_t)(t + 1) * S * 4 * C : nullptr, next ? dc_n : nullptr,
+                                          h->dgifo + (size_t)t * S * 4 * C, dc_t, W + h->off_pi, W + h->off_pf,
+                                          W + h->off_po, S, C, st));
+      }
+      h->launches++;
+    }
+    {
+      Timed tm(h, 5, st);
+      CUDA_TRY(launch_streamed_small_grads(h->dgifo, h->cbuf, h->grads + h->off_bias, num_rows, S, C, st));
+    }
+    h->launches++;
+  } else {
   BwdParams p = h->bp;
   p.I = I; p.C = C; p.R = R; p.S = S; p.T = T;
   p.d = h->d;
@@ -502,7 +577,7 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
     CUDA_TRY(launch_small_grads(h->grads + h->off_bias, h->small_grads, h->d.ngroups, 7 * C, st));
   }
   h->launches++;
-  int rc;
+  }
   // in_diff = DGIFO[1..T] * w_gifo_x                                        (LPS.h:457)
   if (in_diff && (rc = gemm(h, 3, in_diff, (long long)ld_id, num_rows, I, 4 * C, 1.f, h->dgifo, 4 * C, 0,
                             h->params + h->off_wx, I, 0, 0.f, nullptr, st)))
@@ -562,6 +637,7 @@ extern "C" int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* inf
   info->workspace_bytes = h->workspace_bytes;
   info->kernel_launches = h->launches;
   info->gemm_backend = h->gemm_backend;
+  info->weights_streamed = h->streamed ? 1 : 0;
   return 0;
 }
 

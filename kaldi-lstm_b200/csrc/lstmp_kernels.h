@@ -84,6 +84,16 @@ struct ResetMask {
 };
 cudaError_t launch_reset(float* state_c, int C, float* state_r, int R, int S, const ResetMask& m,
                          cudaStream_t stream);
+// weights-streamed mode (lstmp_streamed.cu)
+cudaError_t launch_streamed_fwd_elem(float* gifo_t, const float* c_prev, float* c_out, float* h_t, float* m_t,
+                                     const float* p_i, const float* p_f, const float* p_o, int S, int C,
+                                     cudaStream_t st);
+cudaError_t launch_streamed_bwd_elem(const float* dm, const float* gifo_t, const float* gifo_next, const float* c_t,
+                                     const float* c_prev, const float* h_t, const float* dgifo_next,
+                                     const float* dc_next, float* dgifo_t, float* dc_t, const float* p_i,
+                                     const float* p_f, const float* p_o, int S, int C, cudaStream_t st);
+cudaError_t launch_streamed_small_grads(const float* dgifo, const float* cbuf, float* g_small, int rows, int S, int C,
+                                        cudaStream_t st);
 // strided 2-D copy helper for set/get of pitched caller matrices is done with cudaMemcpy2DAsync.
 
 }  // namespace lstmp

@@ -122,6 +122,23 @@ def test_few_ctas(klb, oracle_mod, monkeypatch):
     run_pair(klb, oracle_mod, I=16, C=100, R=36, S=20, T=4, nchunks=2, scale=0.2, seed=21, check_record=True)
 
 
+def test_weights_streamed_mode_forced(klb, oracle_mod, monkeypatch):
+    """The per-timestep weights-streamed path (used when slices do not fit on chip) gives the same numbers."""
+    from parity_util import run_pair
+    monkeypatch.setenv("LSTMP_B200_FORCE_STREAMED", "1")
+    _, comp, _ = run_pair(klb, oracle_mod, I=40, C=64, R=32, S=4, T=6, nchunks=3, scale=0.2, seed=31, check_record=True,
+                          init_state=True, resets=[None, np.array([0, 1, 0, 0], np.int32), None])
+    assert comp.engine.info()["weights_streamed"] == 1
+
+
+def test_cfg5_shape_2048_1024(klb, oracle_blas):
+    """BASELINE.json configs[4] layer shape (40-in, 2048-cell, 1024-proj): 43 MB of weights do not fit in
+    shared memory -> weights-streamed mode.  Few streams/frames so the CPU oracle stays fast."""
+    from parity_util import run_pair
+    _, comp, _ = run_pair(klb, oracle_blas, I=40, C=2048, R=1024, S=8, T=4, nchunks=2, scale=0.03, seed=32)
+    assert comp.engine.info()["weights_streamed"] == 1
+
+
 def test_growing_chunk_length(klb, oracle_mod):
     """The reference resizes its buffers per call (LPS.h:230); the mirror re-creates the engine."""
     from parity_util import run_pair
