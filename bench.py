@@ -34,6 +34,9 @@ WORKLOADS = {
                         desc="configs[2] first layer only: LstmProjectedStreams 40->800/512, NumStream=64, T=20"),
     "cfg2": dict(layers=[(40, 800, 512)], S=4, T=20,
                  desc="configs[1]: LstmProjectedStreams 40->800/512, NumStream=4, 20-frame BPTT (recipe default)"),
+    "cfg5": dict(layers=[(40, 2048, 1024)], S=64, T=20,
+                 desc="configs[4] per-GPU shape: LstmProjectedStreams 40->2048/1024, NumStream=64 per GPU (512 over 8), "
+                      "T=20 (weights-streamed mode: 43 MB of weights do not fit in shared memory)"),
     "cfg4-lstm": dict(layers=[(40, 800, 512)], S=32, T=20,
                       desc="configs[3] LSTM part: 40->800/512, NumStream=32 per GPU (256 over 8), T=20"),
 }

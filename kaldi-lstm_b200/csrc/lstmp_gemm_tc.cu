@@ -233,32 +233,34 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
 
   if (warp < 8) {
     // =============================== loader / transform ==================================
-    // Two register sets per operand: the global loads of K blocks kb+1 and kb+2 are in flight while
-    // block kb is split and stored, so an L2 round trip is hidden behind a whole loop iteration.
-    Loader<BM, A_MN> la0, la1;
-    Loader<BN, B_MN> lb0, lb1;
+    // Four register sets per operand: the global loads of K blocks kb+1 .. kb+3 are in flight while block kb is split
+    // and stored (ncu: the two-deep version was still stall_long_sb-bound; Little's law needs ~100 KB in flight per SM).
+    constexpr int PF = 4;
+    Loader<BM, A_MN> la0, la1, la2, la3;
+    Loader<BN, B_MN> lb0, lb1, lb2, lb3;
     la0.load(A, lda, m0, M, 0, K, tid);
     lb0.load(B, ldb, n0, N, 0, K, tid);
-    if (nkb > 1) {
-      la1.load(A, lda, m0, M, BK, K, tid);
-      lb1.load(B, ldb, n0, N, BK, K, tid);
-    }
+    if (nkb > 1) { la1.load(A, lda, m0, M, BK, K, tid); lb1.load(B, ldb, n0, N, BK, K, tid); }
+    if (nkb > 2) { la2.load(A, lda, m0, M, 2 * BK, K, tid); lb2.load(B, ldb, n0, N, 2 * BK, K, tid); }
+    if (nkb > 3) { la3.load(A, lda, m0, M, 3 * BK, K, tid); lb3.load(B, ldb, n0, N, 3 * BK, K, tid); }
     auto step = [&](Loader<BM, A_MN>& la, Loader<BN, B_MN>& lb, int kb) {
       const int s = kb % NSTAGE;
       if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
       uint8_t* st = tiles + (size_t)s * SM::STAGE;
       la.store(st, st + SM::A_BYTES, tid);
       lb.store(st + 2 * SM::A_BYTES, st + 2 * SM::A_BYTES + SM::B_BYTES, tid);
-      if (kb + 2 < nkb) {
-        la.load(A, lda, m0, M, (kb + 2) * BK, K, tid);
-        lb.load(B, ldb, n0, N, (kb + 2) * BK, K, tid);
+      if (kb + PF < nkb) {
+        la.load(A, lda, m0, M, (kb + PF) * BK, K, tid);
+        lb.load(B, ldb, n0, N, (kb + PF) * BK, K, tid);
       }
       fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
       mbar_arrive(&full[s]);
     };
-    for (int kb = 0; kb < nkb; kb += 2) {
+    for (int kb = 0; kb < nkb; kb += PF) {
       step(la0, lb0, kb);
       if (kb + 1 < nkb) step(la1, lb1, kb + 1);
+      if (kb + 2 < nkb) step(la2, lb2, kb + 2);
+      if (kb + 3 < nkb) step(la3, lb3, kb + 3);
     }
     // =============================== epilogue ============================================
     mbar_wait(accum_ready, 0);

@@ -185,9 +185,11 @@ size_t fwd_smem_floats(int C, int R, Decomp& d, FwdParams* p, size_t limit_float
     off += (n + 3) & ~size_t(3);
     return (int)o;
   };
-  p->ldwr = R + 4;
+  // row stride = K + 16 floats: for K % 32 == 0 two consecutive rows sit in opposite halves of the 32 banks, so a
+  // warp's LDS.128 over (2 rows x 4 quads) is one wavefront (with K + 4 it was two)
+  p->ldwr = R + 16;
   p->off_wr = take((size_t)4 * d.cpc * p->ldwr);
-  p->ldwm = C + 4;
+  p->ldwm = C + 16;
   p->off_wm = take((size_t)d.rpc * p->ldwm);
   int ldred = 4 * d.cpc > d.rpc ? 4 * d.cpc : d.rpc;
   p->ldred = ldred | 1;
@@ -460,9 +462,9 @@ size_t bwd_smem_floats(int C, int R, Decomp& d, BwdParams* p, size_t limit_float
     return (int)o;
   };
   (void)C;
-  p->ldwr = R + 4;
+  p->ldwr = R + 16;
   p->off_wr = take((size_t)4 * d.cpc * p->ldwr);
-  p->ldwmt = R + 4;
+  p->ldwmt = R + 16;
   p->off_wmt = take((size_t)d.cpc * p->ldwmt);
   p->ldred = d.cpc | 1;
   p->off_red = take((size_t)d.Sg * p->ldred);
