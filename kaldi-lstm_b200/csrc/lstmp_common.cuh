@@ -200,6 +200,7 @@ __device__ __forceinline__ int xbuf_ld(int kch, int ksplit) { return kch + (kspl
 struct SkinnyPlan {          // lives in shared memory; uniform fields + one packed word per thread
   int Sg, Nc, K;
   int n_s_tiles, n_n_tiles, ksplit, npass;
+  int tsz;                   // streams per thread tile: 8 (x 4 columns) for groups of >= 16 streams, else 4
   int ts, tn, nbs, nblocks;  // a warp covers a ts x tn block of tiles; nbs blocks along s; nblocks total
   int kch, nchunks, nslots, ldx, slot_floats;  // ring: slot_floats = Sg*ldx; panel: chunk c at column c*kch
   int panel;                                   // 1: the whole [Sg x K] panel is resident (no slot reuse)
@@ -224,7 +225,12 @@ __device__ __forceinline__ void skinny_tile_of(const SkinnyPlan* pl, int wb, int
 __device__ __forceinline__ void skinny_make_plan(SkinnyPlan* pl, int Sg, int Nc, int K, int cap_floats) {
   const int tid = threadIdx.x;
   if (tid == 0) {
-    const int n_s_tiles = ceil_div(Sg, 4), n_n_tiles = ceil_div(Nc > 0 ? Nc : 1, 4);
+    // The loop is bound by the SM-wide LDS.128 issue rate (one non-uniform 512-byte request per ~4 cycles).  8x4
+    // tiles (12 LDS.128 per 128 FMAs instead of 8 per 64) cut the product time by 15 % but doubled the shuffle
+    // reduction and lost overall (fwd 442 us vs 412 us at S=64), so 4x4 stays the default; see DESIGN.md.
+    const int tsz = 4;
+    pl->tsz = tsz;
+    const int n_s_tiles = ceil_div(Sg, tsz), n_n_tiles = ceil_div(Nc > 0 ? Nc : 1, 4);
     const int tiles = n_s_tiles * n_n_tiles;
     int ks = kThreads / tiles;
     const int ksplit = ks >= 1 ? pow2_floor(ks < 32 ? ks : 32) : 1;
@@ -299,9 +305,10 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ pl, const float* __restrict__ Xg,
-                                                size_t ldX, const float* __restrict__ Ws, int ldw, float* xbuf,
-                                                float* red, int ldred) {
+template <int TS>
+static __device__ __noinline__ void skinny_gemm_t(const SkinnyPlan* __restrict__ pl, const float* __restrict__ Xg,
+                                                  size_t ldX, const float* __restrict__ Ws, int ldw, float* xbuf,
+                                                  float* red, int ldred) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Sg = pl->Sg, Nc = pl->Nc, K = pl->K;
   if (Nc <= 0) return;  // CTA-uniform
@@ -338,20 +345,23 @@ static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ p
       skinny_tile_of(pl, pass * (kThreads / 32) + warp, lane, &active, &s_tile, &n_tile);
     }
     // byte addresses (shared window) of this thread's 4 X rows and 4 W rows, at its first quad
-    uint32_t xa[4], wa[4];
+    uint32_t xa[TS], wa[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TS; ++i) {
       int s = s_tile + i * n_s_tiles;
       xa[i] = smem_u32(xbuf) + (uint32_t)(((s < Sg ? s : Sg - 1) * ldx + 4 * kq) * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
       int n = n_tile + i * n_n_tiles;
       wa[i] = smem_u32(Ws) + (uint32_t)(((n < Nc ? n : Nc - 1) * ldw + 4 * kq) * 4);
     }
     const uint32_t qstep = 16u * ksplit;
     // acc2[i][j] = (sum over even k, sum over odd k) of X[s_i][k] * W[n_j][k]: the natural (x,y) / (z,w) register
     // pairs of the 128-bit loads feed FFMA2 directly, no operand duplication.
-    f32x2 acc2[4][4];
+    f32x2 acc2[TS][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TS; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
 
@@ -375,24 +385,30 @@ static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ p
         const int nq = (K - k0 < kch ? K - k0 : kch) >> 2;
         const uint32_t xoff = (uint32_t)((panel ? k0 : slot * slot_floats) * 4), woff = (uint32_t)(k0 * 4);
         // (a hand software-pipelined variant of this loop measured slower than letting ptxas schedule it)
-        uint32_t x0 = xa[0] + xoff, x1 = xa[1] + xoff, x2 = xa[2] + xoff, x3 = xa[3] + xoff;
-        uint32_t w0 = wa[0] + woff, w1 = wa[1] + woff, w2 = wa[2] + woff, w3 = wa[3] + woff;
+        uint32_t xp[TS], wp[4];
+#pragma unroll
+        for (int i = 0; i < TS; ++i) xp[i] = xa[i] + xoff;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wp[j] = wa[j] + woff;
 #pragma unroll 2
         for (int q = kq; q < nq; q += ksplit) {
-          const float4 xv[4] = {lds128(x0), lds128(x1), lds128(x2), lds128(x3)};
-          const float4 wv[4] = {lds128(w0), lds128(w1), lds128(w2), lds128(w3)};
-          x0 += qstep; x1 += qstep; x2 += qstep; x3 += qstep;
-          w0 += qstep; w1 += qstep; w2 += qstep; w3 += qstep;
-          f32x2 xl[4], xh[4], wl[4], wh[4];
+          f32x2 xl[TS], xh[TS], wl[4], wh[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            xl[i] = pack2(xv[i].x, xv[i].y);
-            xh[i] = pack2(xv[i].z, xv[i].w);
-            wl[i] = pack2(wv[i].x, wv[i].y);
-            wh[i] = pack2(wv[i].z, wv[i].w);
+          for (int i = 0; i < TS; ++i) {
+            const float4 v = lds128(xp[i]);
+            xp[i] += qstep;
+            xl[i] = pack2(v.x, v.y);
+            xh[i] = pack2(v.z, v.w);
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = lds128(wp[j]);
+            wp[j] += qstep;
+            wl[j] = pack2(v.x, v.y);
+            wh[j] = pack2(v.z, v.w);
+          }
+#pragma unroll
+          for (int i = 0; i < TS; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               acc2[i][j] = ffma2(xl[i], wl[j], acc2[i][j]);
@@ -403,9 +419,9 @@ static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ p
       if (++slot == nslots) slot = 0;
     }
     stamp(130);
-    float acc[4][4];
+    float acc[TS][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TS; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float e, o;
@@ -415,13 +431,13 @@ static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ p
     // combine the ksplit partial sums held by adjacent lanes
     for (int off = ksplit >> 1; off >= 1; off >>= 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TS; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], off);
     }
     if (active && kq == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TS; ++i) {
         int s = s_tile + i * n_s_tiles;
         if (s < Sg) {
 #pragma unroll
@@ -435,6 +451,13 @@ static __device__ __noinline__ void skinny_gemm(const SkinnyPlan* __restrict__ p
     __syncthreads();  // the all-gather buffer and red[] are safe to reuse
     stamp(131);
   }
+}
+
+static __device__ __forceinline__ void skinny_gemm(const SkinnyPlan* __restrict__ pl, const float* __restrict__ Xg,
+                                                   size_t ldX, const float* __restrict__ Ws, int ldw, float* xbuf,
+                                                   float* red, int ldred) {
+  if (pl->tsz == 8) skinny_gemm_t<8>(pl, Xg, ldX, Ws, ldw, xbuf, red, ldred);  // CTA-uniform
+  else skinny_gemm_t<4>(pl, Xg, ldX, Ws, ldw, xbuf, red, ldred);
 }
 
 }  // namespace lstmp
