@@ -23,7 +23,8 @@ cudaError_t launch_gemm_simt(float* C, long long ldc, int M, int N, int K, float
 #ifdef LSTMP_HAVE_TC_GEMM
 cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
                            long long lda, int tA, const float* B, long long ldb, int tB, float beta,
-                           const float* bias, cudaStream_t stream, bool* handled);
+                           const float* bias, cudaStream_t stream, bool* handled, float* ws, size_t ws_floats,
+                           int* nlaunch);
 #endif
 }  // namespace lstmp
 
@@ -70,6 +71,8 @@ struct lstmp_b200_engine {
   // weights-streamed mode: slices do not fit in shared memory -> per-step GEMMs + elementwise kernels
   bool streamed = false;
   float *dm = nullptr, *dc2 = nullptr;
+  float* gemm_ws = nullptr;          // split-K partial sums
+  size_t gemm_ws_floats = 0;
   // optional per-kernel event timing
   bool timing = false;
   struct Ev { int kind; cudaEvent_t a, b; };
@@ -143,7 +146,7 @@ extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   float* bufs[] = {h->params, h->corr, h->grads, h->state_c, h->state_r, h->gifo, h->cbuf, h->hbuf,
-                   h->mbuf,   h->rbuf, h->dgifo, h->dr,      h->scratch, h->small_grads, h->dm, h->dc2};
+                   h->mbuf,   h->rbuf, h->dgifo, h->dr,      h->scratch, h->small_grads, h->dm, h->dc2, h->gemm_ws};
   for (float* b : bufs)
     if (b) cudaFree(b);
   if (h->bar) cudaFree(h->bar);
@@ -247,7 +250,8 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
       (rc = alloc_f(&h->scratch, h->streamed ? 4 : (size_t)h->d.ngroups * h->d.ctas_per_group * h->d.Sg * R, &ws)) ||
       (rc = alloc_f(&h->dm, h->streamed ? (size_t)S * C : 4, &ws)) ||
       (rc = alloc_f(&h->dc2, h->streamed ? (size_t)2 * S * C : 4, &ws)) ||
-      (rc = alloc_f(&h->small_grads, (size_t)h->d.ngroups * 7 * C, &ws))) {
+      (rc = alloc_f(&h->small_grads, (size_t)h->d.ngroups * 7 * C, &ws)) ||
+      (rc = alloc_f(&h->gemm_ws, (size_t)4 << 20, &ws))) {
     lstmp_b200_destroy(h);
     return rc;
   }
@@ -257,6 +261,7 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     lstmp_b200_destroy(h);
     return fail((int)e, "barrier counters: %s", cudaGetErrorString(e));
   }
+  h->gemm_ws_floats = env_int("LSTMP_B200_SPLITK", 1) ? ((size_t)4 << 20) : 0;
   h->workspace_bytes = ws;
   h->gemm_backend = 0;
 #ifdef LSTMP_HAVE_TC_GEMM
@@ -420,9 +425,11 @@ static int gemm(lstmp_b200_handle_t h, int kind, float* C, long long ldc, int M,
 #ifdef LSTMP_HAVE_TC_GEMM
   if (h->gemm_backend == 1) {
     bool handled = false;
-    CUDA_TRY(launch_gemm_tc(C, ldc, M, N, K, alpha, A, lda, tA, B, ldb, tB, beta, bias, st, &handled));
+    int nl = 1;
+    CUDA_TRY(launch_gemm_tc(C, ldc, M, N, K, alpha, A, lda, tA, B, ldb, tB, beta, bias, st, &handled, h->gemm_ws,
+                            h->gemm_ws_floats, &nl));
     if (handled) {
-      h->launches++;
+      h->launches += nl;
       return 0;
     }
   }
@@ -710,8 +717,12 @@ extern "C" int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, i
 #ifdef LSTMP_HAVE_TC_GEMM
   if (backend == 1) {
     bool handled = false;
+    int handled_n = 0;
+    static float* dbg_ws = nullptr;   // test hook only: 16 MB split-K workspace, allocated once
+    const size_t dbg_ws_floats = (size_t)4 << 20;
+    if (!dbg_ws && cudaMalloc((void**)&dbg_ws, dbg_ws_floats * sizeof(float)) != cudaSuccess) dbg_ws = nullptr;
     CUDA_TRY(launch_gemm_tc(C, (long long)ldc, M, N, K, alpha, A, (long long)lda, tA, B, (long long)ldb, tB, beta, bias,
-                            st, &handled));
+                            st, &handled, dbg_ws, dbg_ws ? dbg_ws_floats : 0, &handled_n));
     if (!handled) return fail(LSTMP_B200_EUNSUPPORTED, "tcgen05 GEMM does not handle this shape/alignment");
     return 0;
   }

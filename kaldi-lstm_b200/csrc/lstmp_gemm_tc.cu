@@ -196,7 +196,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float alpha,
                const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float beta,
-               const float* __restrict__ bias) {
+               const float* __restrict__ bias, int k_per_split, float* __restrict__ split_ws) {
   using SM = Smem<BN, A_MN, B_MN>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // 128-byte align the tile area
@@ -209,6 +209,19 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (split_ws) {
+    // split-K: slice z of the K range; raw partial sums go to split_ws[z][M x N] and a second kernel reduces them
+    // in a fixed order (deterministic), applying alpha / beta / bias there.
+    const int kb0 = blockIdx.z * k_per_split;
+    A += A_MN ? (size_t)kb0 * lda : (size_t)kb0;
+    B += B_MN ? (size_t)kb0 * ldb : (size_t)kb0;
+    K = (K - kb0 < k_per_split) ? K - kb0 : k_per_split;
+    Cm = split_ws + (size_t)blockIdx.z * M * N;
+    ldc = N;
+    alpha = 1.f;
+    beta = 0.f;
+    bias = nullptr;
+  }
   const int nkb = (K + BK - 1) / BK;
 
   if (tid == 0) {
@@ -345,11 +358,36 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
   }
 }
 
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(float* __restrict__ C, long long ldc, int M, int N,
+                                                            float alpha, float beta, const float* __restrict__ bias,
+                                                            const float* __restrict__ ws, int splits) {
+  const int n4 = N >> 2;
+  const long long total = (long long)M * n4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / n4), n = (int)(idx - (long long)m * n4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + ((size_t)z * M + m) * N + n);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float* c = C + (size_t)m * ldc + n;
+    float o[4] = {alpha * a.x, alpha * a.y, alpha * a.z, alpha * a.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (beta != 0.f) o[q] += beta * c[q];
+      if (bias) o[q] += bias[n + q];
+      c[q] = o[q];
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
                               long long lda, const float* B, long long ldb, float beta, const float* bias,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, float* ws, size_t ws_floats, int* nlaunch) {
   using SM = Smem<BN, A_MN, B_MN>;
+  *nlaunch = 1;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -361,8 +399,31 @@ static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, floa
     attr_set[dev & 63] = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM), block(THREADS);
+  // split-K when the output tiles alone cannot fill the 148 SMs (e.g. in_diff: 40 tiles, G(w_r_m): 28 tiles)
+  const int tiles = grid.x * grid.y, nkb = (K + BK - 1) / BK;
+  int splits = 1;
+  if (ws && tiles < 100 && nkb >= 8 && (N & 3) == 0) {
+    splits = 148 / tiles;
+    if (splits > 8) splits = 8;
+    if (splits > nkb / 4) splits = nkb / 4;
+    while (splits > 1 && (size_t)splits * M * N > ws_floats) --splits;
+  }
+  if (splits > 1) {
+    const int kbs = (nkb + splits - 1) / splits;        // K blocks per split
+    splits = (nkb + kbs - 1) / kbs;                      // drop empty tail splits
+    grid.z = splits;
+    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
+                                                                       bias, kbs * BK, ws);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return e2;
+    int rb = (int)(((long long)M * (N >> 2) + 255) / 256);
+    if (rb > 148 * 4) rb = 148 * 4;
+    splitk_reduce_kernel<<<rb, 256, 0, stream>>>(C, ldc, M, N, alpha, beta, bias, ws, splits);
+    *nlaunch = 2;
+    return cudaGetLastError();
+  }
   gemm_tc_kernel<BN, A_MN, B_MN><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
-                                                                     bias);
+                                                                     bias, 0, nullptr);
   return cudaGetLastError();
 }
 }  // namespace tc
@@ -372,7 +433,7 @@ static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, floa
 // (n contiguous -> MN-major); tB == 1: B stored [N x K] (k contiguous -> K-major).
 cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float alpha, const float* A, long long lda,
                            int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
-                           cudaStream_t stream, bool* handled) {
+                           cudaStream_t stream, bool* handled, float* ws, size_t ws_floats, int* nlaunch) {
   *handled = false;
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -387,7 +448,7 @@ cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float a
   *handled = true;
   const bool small_n = (N <= 64);
 #define LSTMP_TC_CASE(BN_, AMN_, BMN_) \
-  return tc::launch_one<BN_, AMN_, BMN_>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream)
+  return tc::launch_one<BN_, AMN_, BMN_>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, ws_floats, nlaunch)
   if (small_n) {
     if (!a_mn && !b_mn) LSTMP_TC_CASE(64, false, false);
     if (!a_mn && b_mn) LSTMP_TC_CASE(64, false, true);
