@@ -344,6 +344,13 @@ static __device__ __noinline__ void skinny_gemm_t(const SkinnyPlan* __restrict__
     } else {
       skinny_tile_of(pl, pass * (kThreads / 32) + warp, lane, &active, &s_tile, &n_tile);
     }
+    issue_slot = 0;
+    issue_k0 = 0;
+    int issued = 0;
+    stamp(100);
+    for (; issued < nslots && issued < nchunks; ++issued) issue();
+    stamp(101);
+    // (address set-up below overlaps with the L2 round trip of the chunks just issued)
     // byte addresses (shared window) of this thread's 4 X rows and 4 W rows, at its first quad
     uint32_t xa[TS], wa[4];
 #pragma unroll
@@ -365,12 +372,6 @@ static __device__ __noinline__ void skinny_gemm_t(const SkinnyPlan* __restrict__
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
 
-    issue_slot = 0;
-    issue_k0 = 0;
-    int issued = 0;
-    stamp(100);
-    for (; issued < nslots && issued < nchunks; ++issued) issue();
-    stamp(101);
     int slot = 0;
     for (int c = 0; c < nchunks; ++c) {
       cp_async_wait_dyn(issued - c - 1);

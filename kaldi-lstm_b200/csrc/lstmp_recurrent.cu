@@ -218,47 +218,54 @@ cudaError_t launch_fwd(const FwdParams& p, size_t smem_bytes, cudaStream_t strea
 // =========================================================================================
 
 // P[s][k] = sum_{n<Nc} dT[n][s] * W[n][k]   (partial d_r over my gate rows; LPS.h:391 restricted
-// to the rows of W_gifo_r this CTA holds).  8 streams x 4 k register tile, result to global.
+// to the rows of W_gifo_r this CTA holds).  8 streams x 8 k register tile per thread (two lane-contiguous
+// quads of k, R/2 apart), result to global.  The loop is bound by LDS.128 issue (one W request is shared by
+// 8 streams here, by 8 streams x 4 k before: the 8x8 tile halves the requests per FMA); the weight pairs
+// (k, k+1) come straight from the 128-bit loads, the stream value is duplicated into an FFMA2 operand pair.
 __device__ __forceinline__ void outer_gemm(const float* __restrict__ dT, int ldd, const float* __restrict__ Ws,
                                            int ldw, int Nc, int Sg, int R, float* __restrict__ P) {
-  const int nkq = R >> 2;
+  const int nkq = R >> 2;           // quads along k
+  const int half = (nkq + 1) >> 1;  // a thread owns quads kq and kq + half (the second one may not exist: R % 8 == 4)
   const int nst = ceil_div(Sg, 8);
-  const int tiles = nkq * nst;
+  const int tiles = half * nst;
   for (int tile = threadIdx.x; tile < tiles; tile += kThreads) {
-    const int kq = tile % nkq, st = tile / nkq;
-    // acc2[p][c] = (P[2p][c], P[2p+1][c]): stream pairs come straight from the 128-bit loads of dT, the weight
-    // component is duplicated once per n (4 packs per 16 FFMA2).
-    f32x2 acc2[4][4];
+    const int kq = tile % half, st = tile / half;
+    f32x2 acc2[8][4];  // [stream][k pair]: pairs 0,1 = quad kq, pairs 2,3 = quad kq + half
 #pragma unroll
-    for (int pq = 0; pq < 4; ++pq)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc2[pq][c] = 0ull;
-    const float* wp = Ws + 4 * kq;
+      for (int c = 0; c < 4; ++c) acc2[i][c] = 0ull;
+    const bool has2 = kq + half < nkq;
+    const float* wp0 = Ws + 4 * kq;
+    const float* wp1 = has2 ? Ws + 4 * (kq + half) : wp0;
     const float* dp = dT + 8 * st;
 #pragma unroll 2
     for (int n = 0; n < Nc; ++n) {
-      float4 w = *reinterpret_cast<const float4*>(wp + (size_t)n * ldw);
-      float4 d0 = *reinterpret_cast<const float4*>(dp + (size_t)n * ldd);
-      float4 d1 = *reinterpret_cast<const float4*>(dp + (size_t)n * ldd + 4);
-      const f32x2 dv[4] = {pack2(d0.x, d0.y), pack2(d0.z, d0.w), pack2(d1.x, d1.y), pack2(d1.z, d1.w)};
-      const f32x2 wv[4] = {pack2(w.x, w.x), pack2(w.y, w.y), pack2(w.z, w.z), pack2(w.w, w.w)};
+      const float4 w0 = *reinterpret_cast<const float4*>(wp0 + (size_t)n * ldw);
+      const float4 w1 = *reinterpret_cast<const float4*>(wp1 + (size_t)n * ldw);
+      const float4 d0 = *reinterpret_cast<const float4*>(dp + (size_t)n * ldd);
+      const float4 d1 = *reinterpret_cast<const float4*>(dp + (size_t)n * ldd + 4);
+      const f32x2 wv[4] = {pack2(w0.x, w0.y), pack2(w0.z, w0.w), pack2(w1.x, w1.y), pack2(w1.z, w1.w)};
+      const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-      for (int pq = 0; pq < 4; ++pq)
+      for (int i = 0; i < 8; ++i) {
+        const f32x2 dd = pack2(dv[i], dv[i]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc2[pq][c] = ffma2(dv[pq], wv[c], acc2[pq][c]);
-    }
-    float4 acc[8];
-#pragma unroll
-    for (int pq = 0; pq < 4; ++pq) {
-      unpack2(acc2[pq][0], acc[2 * pq].x, acc[2 * pq + 1].x);
-      unpack2(acc2[pq][1], acc[2 * pq].y, acc[2 * pq + 1].y);
-      unpack2(acc2[pq][2], acc[2 * pq].z, acc[2 * pq + 1].z);
-      unpack2(acc2[pq][3], acc[2 * pq].w, acc[2 * pq + 1].w);
+        for (int c = 0; c < 4; ++c) acc2[i][c] = ffma2(dd, wv[c], acc2[i][c]);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      int s = 8 * st + i;
-      if (s < Sg) *reinterpret_cast<float4*>(P + (size_t)s * R + 4 * kq) = acc[i];
+      const int sr = 8 * st + i;
+      if (sr < Sg) {
+        float4 o0, o1;
+        unpack2(acc2[i][0], o0.x, o0.y);
+        unpack2(acc2[i][1], o0.z, o0.w);
+        unpack2(acc2[i][2], o1.x, o1.y);
+        unpack2(acc2[i][3], o1.z, o1.w);
+        *reinterpret_cast<float4*>(P + (size_t)sr * R + 4 * kq) = o0;
+        if (has2) *reinterpret_cast<float4*>(P + (size_t)sr * R + 4 * (kq + half)) = o1;
+      }
     }
   }
 }
@@ -349,10 +356,20 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_kernel(const __grid_con
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool on = (pg < npg);
         if (on && have_next) {
+          // batches of 12 independent L2 loads, then the (fixed-order) adds: one load per add would serialise the
+          // ~700-cycle L2 round trips (the stamps showed 7-9 k cycles for this phase)
           const float* src = grp_scratch + e0 + 4 * (cb + col);
-          for (int q = pg; q < nprod; q += npg) {
-            float4 v = ld_cg_f4(src + (size_t)q * nper);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          for (int q = pg; q < nprod; q += 12 * npg) {
+            float4 v[12];
+#pragma unroll
+            for (int u = 0; u < 12; ++u) {
+              const int qq = q + u * npg;
+              v[u] = qq < nprod ? ld_cg_f4(src + (size_t)qq * nper) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 12; ++u) {
+              a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
+            }
           }
         }
         float4* rb = reinterpret_cast<float4*>(xbuf);
