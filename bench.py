@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the extra cfg2 (NumStream=4) measurement")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -399,7 +400,7 @@ def main():
                                       n, dt, stack.blas, stack.threads, os.cpu_count())}
 
     secondary = None
-    if rank == 0 and world == 1 and args.workload == "cfg3":
+    if rank == 0 and world == 1 and args.workload == "cfg3" and not args.no_secondary:
         # BASELINE.json configs[1] (NumStream=4, the shipped recipe's default) measured in the same run, device-resident
         try:
             wl2 = WORKLOADS["cfg2"]

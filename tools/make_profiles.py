@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Regenerate profiles/ from the two ncu passes of B200_PROFILING.md:
+
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_rN.csv \
+      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
+  ncu --set full --clock-control none --import-source on -k regex:"lstmp_.*_kernel|gemm_tc_kernel" -s 14 -c 12 \
+      -o gpurun_out/prof_rN python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
+
+usage: tools/make_profiles.py <round> [launches.csv] [prof.ncu-rep]
+writes profiles/rN_launches.csv, rN_launch_summary.md, rN_ncu_set_full_selected.csv, traffic.json
+"""
+import collections
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SELECTED = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "lts__t_sector_hit_rate.pct",
+]
+
+
+def short(name):
+    return name.split("(")[0][:60]
+
+
+def launch_summary(rnd, path):
+    rows = [l for l in open(path) if l.startswith('"')]
+    rd = csv.DictReader(io.StringIO("".join(rows)))
+    tot = collections.OrderedDict()
+    nrand = 0
+    for r in rd:
+        if r["Metric Name"] != "gpu__time_duration.sum":
+            continue
+        # bench.py's secondary cfg2 measurement (absent with --no-secondary) starts with its own torch.randn inputs:
+        # the summary covers the cfg3 workload only, i.e. the launches before the third normal-distribution kernel
+        if "distribution_elementwise" in r["Kernel Name"]:
+            nrand += 1
+            if nrand > 2:
+                break
+        v = float(r["Metric Value"].replace(",", ""))
+        if r["Metric Unit"] in ("ns", "nsecond"):
+            v /= 1e3
+        elif r["Metric Unit"] in ("ms", "msecond"):
+            v *= 1e3
+        k = short(r["Kernel Name"])
+        t = tot.setdefault(k, [0, 0.0])
+        t[0] += 1
+        t[1] += v
+    allus = sum(v[1] for v in tot.values())
+    out = ["# Round %s launch list summary (ncu --metrics gpu__time_duration.sum --clock-control none, "
+           "bench.py --steps 3 --warmup 3, workload cfg3:\n3 warm-up + 3 timed + 3 per-kernel-timing steps; the secondary "
+           "cfg2 launches that follow in the raw CSV are excluded)" % rnd, "",
+           "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
+           "| kernel | launches | total us | share |", "|---|---|---|---|"]
+    for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        out.append("| %s | %d | %.1f | %.3f |" % (k, n, us, us / allus))
+    open(os.path.join(ROOT, "profiles", "r%s_launch_summary.md" % rnd), "w").write("\n".join(out) + "\n")
+    with open(os.path.join(ROOT, "profiles", "r%s_launches.csv" % rnd), "w") as f:
+        f.write("".join(rows))
+    return tot
+
+
+def full_selected(rnd, rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True,
+                         check=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    keep = ["Kernel Name"] + [m for m in SELECTED if m in col]
+    with open(os.path.join(ROOT, "profiles", "r%s_ncu_set_full_selected.csv" % rnd), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(keep)
+        w.writerow([units[col[k]] for k in keep])
+        for r in data:
+            w.writerow([r[col[k]] for k in keep])
+
+    def tobytes(v, unit):
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+    acc = collections.defaultdict(list)
+    for r in data:
+        name = r[col["Kernel Name"]]
+        key = ("fwd_recurrent" if "lstmp_fwd_kernel" in name else "bwd_recurrent" if "lstmp_bwd_kernel" in name
+               else "gemm_tc" if "gemm_tc_kernel" in name else None)
+        if key is None:
+            continue
+        acc[key].append(tobytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) +
+                        tobytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]]))
+    traffic = {k: sum(v) / len(v) for k, v in acc.items()}
+    traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the launches captured by "
+                        "ncu --set full (profiles/r%s_ncu_set_full_selected.csv); bench workload cfg3, round %s"
+                        % (rnd, rnd))
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    return traffic
+
+
+if __name__ == "__main__":
+    rnd = sys.argv[1] if len(sys.argv) > 1 else "1"
+    lcsv = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches_r%s.csv" % rnd)
+    rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "prof_r%s.ncu-rep" % rnd)
+    print(launch_summary(rnd, lcsv))
+    print(full_selected(rnd, rep))
