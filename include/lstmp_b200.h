@@ -131,6 +131,7 @@ typedef struct {
   unsigned long long kernel_launches; /* kernels launched by this handle so far */
   int gemm_backend;                /* 0 = fp32 SIMT, 1 = tcgen05 3xTF32 */
   int weights_streamed;            /* 1: weight slices do not fit in shared memory; per-timestep GEMM path */
+  int fwd_tensor_core;             /* 1: the forward time loop runs on tcgen05 (num_stream <= 64), 0: FP32 FFMA */
 } lstmp_b200_info_t;
 int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* info);
 

@@ -63,6 +63,11 @@ struct lstmp_b200_engine {
   FwdParams fp{};
   BwdParams bp{};
   size_t fwd_smem = 0, bwd_smem = 0;
+  // tensor-core forward time loop (num_stream <= 64): own decomposition (one stream group) and barrier counter
+  bool fwd_tc = false;
+  FwdTcParams ftp{};
+  size_t fwd_tc_smem = 0;
+  unsigned bar_base_tc = 0;
   int T_last = 0;        // frames of the last propagate (0 = none)
   bool have_bwd = false; // a backpropagate record exists for T_last
   unsigned long long launches = 0;
@@ -226,6 +231,16 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
       delete h;
       return fail((int)e, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e));
     }
+    if (env_int("LSTMP_B200_TC_FWD", 1) && h->d.ngroups * h->d.ctas_per_group == sm_use) {
+      FwdTcParams t{};
+      size_t sz = 0;
+      if (fwd_tc_plan(C, R, S, sm_use, smem_limit, &t, &sz) && fwd_tc_set_smem_limit(sz) == cudaSuccess) {
+        h->fwd_tc = true;
+        t.stagger = env_int("LSTMP_B200_TC_STAGGER", 1);
+        h->ftp = t;
+        h->fwd_tc_smem = sz;
+      }
+    }
   }
 
   // arenas
@@ -255,8 +270,8 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     lstmp_b200_destroy(h);
     return rc;
   }
-  e = cudaMalloc((void**)&h->bar, (size_t)kMaxGroupsHost * kBarStride * sizeof(unsigned));
-  if (e == cudaSuccess) e = cudaMemset(h->bar, 0, (size_t)kMaxGroupsHost * kBarStride * sizeof(unsigned));
+  e = cudaMalloc((void**)&h->bar, (size_t)(kMaxGroupsHost + 1) * kBarStride * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(h->bar, 0, (size_t)(kMaxGroupsHost + 1) * kBarStride * sizeof(unsigned));
   if (e != cudaSuccess) {
     lstmp_b200_destroy(h);
     return fail((int)e, "barrier counters: %s", cudaGetErrorString(e));
@@ -487,6 +502,33 @@ extern "C" int lstmp_b200_propagate(lstmp_b200_handle_t h, const float* in, size
     h->have_bwd = false;
     return 0;
   }
+  if (h->fwd_tc) {
+    FwdTcParams q = h->ftp;
+    q.I = I; q.C = C; q.R = R; q.S = S; q.T = T;
+    q.w_gifo_r = h->params + h->off_wr;
+    q.w_r_m = h->params + h->off_wm;
+    q.p_i = h->params + h->off_pi;
+    q.p_f = h->params + h->off_pf;
+    q.p_o = h->params + h->off_po;
+    q.gifo = h->gifo; q.cbuf = h->cbuf; q.hbuf = h->hbuf; q.mbuf = h->mbuf; q.rbuf = h->rbuf;
+    q.out = out;
+    q.ld_out = (long long)ld_out;
+    q.state_c = h->state_c;
+    q.state_r = h->state_r;
+    q.bar = h->bar + (size_t)kMaxGroupsHost * kBarStride;
+    q.bar_base = h->bar_base_tc;
+    q.dbg = h->d.dbg;
+    q.dbg_stamps = h->dbg_stamps;
+    {
+      Timed tm(h, 1, st);
+      CUDA_TRY(launch_fwd_tc(q, h->fwd_tc_smem, st));
+    }
+    h->launches++;
+    h->bar_base_tc += (unsigned)(fwd_barriers(T) * q.nctas);
+    h->T_last = T;
+    h->have_bwd = false;
+    return 0;
+  }
   FwdParams p = h->fp;
   p.I = I; p.C = C; p.R = R; p.S = S; p.T = T;
   p.d = h->d;
@@ -645,6 +687,7 @@ extern "C" int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* inf
   info->kernel_launches = h->launches;
   info->gemm_backend = h->gemm_backend;
   info->weights_streamed = h->streamed ? 1 : 0;
+  info->fwd_tensor_core = h->fwd_tc ? 1 : 0;
   return 0;
 }
 

@@ -23,77 +23,20 @@
 // 3-stage shared-memory ring, mbarrier full/empty handshakes, accumulator in TMEM.
 #include "lstmp_common.cuh"
 #include "lstmp_kernels.h"
+#include "lstmp_tc.cuh"
 
 namespace lstmp {
 
 namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;        // fp32 elements per stage along K (= 4 MMAs of K=8)
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 2;      // UMMA operand stages (hi/lo tiles of A and B)
+constexpr int NRAW = 3;        // K blocks of raw fp32 operands in flight per CTA (cp.async landing slots)
 constexpr int LOADERS = 256;  // warps 0-7
 constexpr int THREADS = LOADERS + 32;
 
-// Shared-memory tile geometry (bytes).  rows = BM or BN.
-// K-major  : off(r,k) = (k/4)*LBO + (r/8)*128 + (r%8)*16 + (k%4)*4     LBO = rows*16 + 16 (odd # of 16B units)
-// MN-major : off(r,k) = (r/4)*SBO + (r%4)*4 + (k%8)*16 + (k/8)*LBO      SBO = 144, LBO = (rows/4)*144
-__host__ __device__ constexpr uint32_t kmaj_lbo(int rows) { return rows * 16 + 16; }
-__host__ __device__ constexpr uint32_t kmaj_bytes(int rows) { return (BK / 4) * kmaj_lbo(rows); }
-__host__ __device__ constexpr uint32_t mnmaj_sbo() { return 144; }
-__host__ __device__ constexpr uint32_t mnmaj_lbo(int rows) { return (rows / 4) * mnmaj_sbo(); }
-__host__ __device__ constexpr uint32_t mnmaj_bytes(int rows) { return (BK / 8) * mnmaj_lbo(rows); }
-__host__ __device__ constexpr uint32_t tile_bytes(int rows, bool mn) {
-  return ((mn ? mnmaj_bytes(rows) : kmaj_bytes(rows)) + 127u) & ~127u;
-}
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
-  // layout_type SWIZZLE_NONE=0 [61,64)
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Global operand load that the compiler may not sink towards its use: the point of the two register sets is
-// that these loads are ISSUED two K blocks ahead (ncu showed stall_long_sb on the first use otherwise).
-__device__ __forceinline__ float4 ldg_early(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
+// operand tiles are SWIZZLE_128B K-major (lstmp_tc.cuh): rows x 128 bytes, dense
+__host__ __device__ constexpr uint32_t tile_bytes(int rows, bool) { return (uint32_t)rows * 128u; }
 
 // One operand's loader state.  The shared-memory tile is ALWAYS K-major (the layout validated on
 // hardware); a source stored with the M/N index contiguous ("MN-major", e.g. DGIFO^T for the weight
@@ -104,19 +47,25 @@ struct Loader {
   static constexpr int UNITS = ROWS * (BK / 4) / LOADERS;              // float4 units per thread (K-major source)
   static constexpr int NBLK = (ROWS / 4) * (BK / 4);                    // 4x4 blocks per tile (MN-major source)
   static constexpr int BPT = (NBLK + LOADERS - 1) / LOADERS;            // blocks per thread
-  float4 v[MN ? BPT * 4 : UNITS];
+  static constexpr int NV = MN ? BPT * 4 : UNITS;                       // 16-byte units this thread owns per K block
+  static constexpr uint32_t RAW_BYTES = (uint32_t)NV * LOADERS * 16;    // raw landing slot of one K block
+  float4 v[NV];
 
-  __device__ __forceinline__ void load(const float* __restrict__ src, long long ld, int row0, int nrows, int k0,
-                                       int K, int tid) {
+  // Stage 1: cp.async (LDGSTS, tracked by cp.async groups, NRAW K blocks in flight) of this thread's units of the K
+  // block at k0 into ITS OWN 16-byte slots of `raw`.  (Prefetching into rotating register sets was ~4x slower: with 32
+  // LDG.128 in flight per thread the 6 scoreboards are shared and every wait also waited for the newest loads.)
+  __device__ __forceinline__ void issue(uint8_t* raw, const float* __restrict__ src, long long ld, int row0,
+                                        int nrows, int k0, int K, int tid) const {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!MN) {
 #pragma unroll
       for (int i = 0; i < UNITS; ++i) {
         const int u = tid + i * LOADERS;
         const int kc = u % (BK / 4), r = u / (BK / 4);
         const int gr = row0 + r, gk = k0 + 4 * kc;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < nrows && gk < K) x = ldg_early(src + (size_t)gr * ld + gk);
-        v[i] = x;
+        uint8_t* dst = raw + (size_t)u * 16;
+        if (gr < nrows && gk < K) cp_async16(dst, src + (size_t)gr * ld + gk);
+        else *reinterpret_cast<float4*>(dst) = z;
       }
     } else {
       // blocks of 4 k x 4 mn: block b -> mn-block mb = b % (ROWS/4), k-chunk kc = b / (ROWS/4)
@@ -128,11 +77,21 @@ struct Loader {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int gk = k0 + 4 * kc + kk;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (b < NBLK && gr < nrows && gk < K) x = ldg_early(src + (size_t)gk * ld + gr);
-          v[blk * 4 + kk] = x;  // row kk of the block: 4 consecutive mn at k = 4kc+kk
+          uint8_t* dst = raw + ((size_t)(blk * 4 + kk) * LOADERS + tid) * 16;
+          if (b < NBLK && gr < nrows && gk < K) cp_async16(dst, src + (size_t)gk * ld + gr);
+          else *reinterpret_cast<float4*>(dst) = z;  // row kk of the block: 4 consecutive mn at k = 4kc+kk
         }
       }
+    }
+  }
+  // Stage 2a: read this thread's own units back (after cp.async.wait_group)
+  __device__ __forceinline__ void fetch(const uint8_t* raw, int tid) {
+    if (!MN) {
+#pragma unroll
+      for (int i = 0; i < UNITS; ++i) v[i] = *reinterpret_cast<const float4*>(raw + (size_t)(tid + i * LOADERS) * 16);
+    } else {
+#pragma unroll
+      for (int i = 0; i < BPT * 4; ++i) v[i] = *reinterpret_cast<const float4*>(raw + ((size_t)i * LOADERS + tid) * 16);
     }
   }
 
@@ -156,7 +115,7 @@ struct Loader {
       for (int i = 0; i < UNITS; ++i) {
         const int u = tid + i * LOADERS;
         const int kc = u % (BK / 4), r = u / (BK / 4);
-        split_store(hi, lo, kc * kmaj_lbo(ROWS) + (r >> 3) * 128 + (r & 7) * 16, v[i]);
+        split_store(hi, lo, sw128_off(r, kc), v[i]);
       }
     } else {
 #pragma unroll
@@ -177,7 +136,7 @@ struct Loader {
           const int i = (t + rot) & 3;
           const float4 c = (i == 0) ? c0 : (i == 1) ? c1 : (i == 2) ? c2 : c3;
           const int r = 4 * mb + i;
-          split_store(hi, lo, kc * kmaj_lbo(ROWS) + (r >> 3) * 128 + (r & 7) * 16, c);
+          split_store(hi, lo, sw128_off(r, kc), c);
         }
       }
     }
@@ -189,7 +148,9 @@ struct Smem {
   static constexpr uint32_t A_BYTES = tile_bytes(BM, false);
   static constexpr uint32_t B_BYTES = tile_bytes(BN, false);
   static constexpr uint32_t STAGE = 2 * A_BYTES + 2 * B_BYTES;  // A_hi | A_lo | B_hi | B_lo
-  static constexpr uint32_t TOTAL = NSTAGE * STAGE + 1024;       // + barriers / tmem slot / alignment slack
+  static constexpr uint32_t RAW_A = Loader<BM, A_MN>::RAW_BYTES, RAW_B = Loader<BN, B_MN>::RAW_BYTES;
+  static constexpr uint32_t RAW = RAW_A + RAW_B;                 // one K block of raw fp32 operands
+  static constexpr uint32_t TOTAL = NSTAGE * STAGE + NRAW * RAW + 2048;  // + barriers / tmem slot + alignment slack
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -199,15 +160,16 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
                const float* __restrict__ bias, int k_per_split, float* __restrict__ split_ws) {
   using SM = Smem<BN, A_MN, B_MN>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // 128-byte align the tile area
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * SM::STAGE);
+  // 1024-byte align the tile area (SWIZZLE_128B atoms)
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* raw = tiles + NSTAGE * SM::STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(raw + NRAW * SM::RAW);
   uint64_t* empty = full + NSTAGE;
   uint64_t* accum_ready = empty + NSTAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (keeps the issuer's operands in URs)
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (split_ws) {
     // split-K: slice z of the K range; raw partial sums go to split_ws[z][M x N] and a second kernel reduces them
@@ -226,7 +188,7 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], LOADERS);
+      mbar_init(&full[s], LOADERS / 32);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum_ready, 1);
@@ -242,38 +204,41 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp < 8) {
     // =============================== loader / transform ==================================
-    // Four register sets per operand: the global loads of K blocks kb+1 .. kb+3 are in flight while block kb is split
-    // and stored (ncu: the two-deep version was still stall_long_sb-bound; Little's law needs ~100 KB in flight per SM).
-    constexpr int PF = 4;
-    Loader<BM, A_MN> la0, la1, la2, la3;
-    Loader<BN, B_MN> lb0, lb1, lb2, lb3;
-    la0.load(A, lda, m0, M, 0, K, tid);
-    lb0.load(B, ldb, n0, N, 0, K, tid);
-    if (nkb > 1) { la1.load(A, lda, m0, M, BK, K, tid); lb1.load(B, ldb, n0, N, BK, K, tid); }
-    if (nkb > 2) { la2.load(A, lda, m0, M, 2 * BK, K, tid); lb2.load(B, ldb, n0, N, 2 * BK, K, tid); }
-    if (nkb > 3) { la3.load(A, lda, m0, M, 3 * BK, K, tid); lb3.load(B, ldb, n0, N, 3 * BK, K, tid); }
-    auto step = [&](Loader<BM, A_MN>& la, Loader<BN, B_MN>& lb, int kb) {
+    Loader<BM, A_MN> la;
+    Loader<BN, B_MN> lb;
+#pragma unroll
+    for (int i = 0; i < NRAW; ++i) {
+      if (i < nkb) {
+        la.issue(raw + i * SM::RAW, A, lda, m0, M, i * BK, K, tid);
+        lb.issue(raw + i * SM::RAW + SM::RAW_A, B, ldb, n0, N, i * BK, K, tid);
+      }
+      cp_async_commit();
+    }
+    int rs = 0;  // raw slot of K block kb
+    for (int kb = 0; kb < nkb; ++kb) {
+      cp_async_wait<NRAW - 1>();  // this thread's copies of K block kb have landed
+      uint8_t* rw = raw + rs * SM::RAW;
+      la.fetch(rw, tid);
+      lb.fetch(rw + SM::RAW_A, tid);
+      if (kb + NRAW < nkb) {
+        la.issue(rw, A, lda, m0, M, (kb + NRAW) * BK, K, tid);
+        lb.issue(rw + SM::RAW_A, B, ldb, n0, N, (kb + NRAW) * BK, K, tid);
+      }
+      cp_async_commit();  // one group per K block (possibly empty) keeps the wait_group arithmetic uniform
+      if (++rs == NRAW) rs = 0;
       const int s = kb % NSTAGE;
       if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
       uint8_t* st = tiles + (size_t)s * SM::STAGE;
       la.store(st, st + SM::A_BYTES, tid);
       lb.store(st + 2 * SM::A_BYTES, st + 2 * SM::A_BYTES + SM::B_BYTES, tid);
-      if (kb + PF < nkb) {
-        la.load(A, lda, m0, M, (kb + PF) * BK, K, tid);
-        lb.load(B, ldb, n0, N, (kb + PF) * BK, K, tid);
-      }
-      fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-      mbar_arrive(&full[s]);
-    };
-    for (int kb = 0; kb < nkb; kb += PF) {
-      step(la0, lb0, kb);
-      if (kb + 1 < nkb) step(la1, lb1, kb + 1);
-      if (kb + 2 < nkb) step(la2, lb2, kb + 2);
-      if (kb + 3 < nkb) step(la3, lb3, kb + 3);
+      // The proxy fence lives on the consumer side (MMA warp, after its acquire-wait): here it would compile to
+      // MEMBAR.ALL.CTA and wait for the copies of the next K blocks.  One arrival per warp.
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&full[s]);
     }
     // =============================== epilogue ============================================
     mbar_wait(accum_ready, 0);
@@ -329,23 +294,25 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % NSTAGE;
       mbar_wait(&full[s], (uint32_t)((kb / NSTAGE) & 1));
+      fence_async_smem();  // loaders' generic-proxy stores (ordered by the mbarrier) -> tensor core's async proxy
       tc_fence_after();
-      if ((tid & 31) == 0) {
+      {
+        // the whole warp runs the burst on warp-uniform operands; elect.sync predicates the instructions (lstmp_tc.cuh)
         const uint32_t a_hi = tiles_s + s * SM::STAGE, a_lo = a_hi + SM::A_BYTES;
         const uint32_t b_hi = a_hi + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
-          // MMA j covers the 16-byte K chunks 2j and 2j+1 (K = 8 tf32 per instruction)
-          const uint32_t a_off = 2 * j * kmaj_lbo(BM), b_off = 2 * j * kmaj_lbo(BN);
-          const uint32_t a_l = kmaj_lbo(BM), a_s = 128u, b_l = kmaj_lbo(BN), b_s = 128u;
-          const uint64_t dah = make_desc(a_hi + a_off, a_l, a_s), dal = make_desc(a_lo + a_off, a_l, a_s);
-          const uint64_t dbh = make_desc(b_hi + b_off, b_l, b_s), dbl = make_desc(b_lo + b_off, b_l, b_s);
-          mma_tf32(tmem_base, dal, dbh, idesc, (kb | j) ? 1u : 0u);  // small terms first
-          mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          // MMA j covers the 16-byte K chunks 2j and 2j+1 of the 128-byte swizzled rows (K = 8 tf32 per instruction)
+          const uint64_t dah = make_desc_sw128(a_hi + 32 * j), dal = make_desc_sw128(a_lo + 32 * j);
+          const uint64_t dbh = make_desc_sw128(b_hi + 32 * j), dbl = make_desc_sw128(b_lo + 32 * j);
+          if (elect_one()) mma_tf32(tmem_base, dal, dbh, idesc, (kb | j) ? 1u : 0u);  // small terms first
+          if (elect_one()) mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          if (elect_one()) mma_tf32(tmem_base, dah, dbh, idesc, 1u);
         }
-        umma_commit(&empty[s]);                       // frees the stage once these MMAs have read it
-        if (kb == nkb - 1) umma_commit(accum_ready);  // accumulator complete
+        if (elect_one()) {
+          umma_commit(&empty[s]);                       // frees the stage once these MMAs have read it
+          if (kb == nkb - 1) umma_commit(accum_ready);  // accumulator complete
+        }
       }
       __syncwarp();
     }

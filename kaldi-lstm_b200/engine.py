@@ -35,7 +35,7 @@ class Info(ctypes.Structure):
         ("cells_per_cta", ctypes.c_int), ("rcols_per_cta", ctypes.c_int),
         ("fwd_smem_bytes", ctypes.c_size_t), ("bwd_smem_bytes", ctypes.c_size_t),
         ("workspace_bytes", ctypes.c_size_t), ("kernel_launches", ctypes.c_ulonglong),
-        ("gemm_backend", ctypes.c_int), ("weights_streamed", ctypes.c_int),
+        ("gemm_backend", ctypes.c_int), ("weights_streamed", ctypes.c_int), ("fwd_tensor_core", ctypes.c_int),
     ]
 
 

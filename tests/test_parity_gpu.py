@@ -111,8 +111,33 @@ def test_stream_group_decompositions(klb, oracle_blas, ngroups, monkeypatch):
     """The same maths under every work decomposition the engine can pick."""
     from parity_util import run_pair
     monkeypatch.setenv("LSTMP_B200_NGROUPS", str(ngroups))
+    monkeypatch.setenv("LSTMP_B200_TC_FWD", "0")  # the FP32 FFMA forward kernel under every decomposition
     _, comp, _ = run_pair(klb, oracle_blas, I=40, C=256, R=128, S=64, T=6, nchunks=2, scale=0.08, seed=12 + ngroups)
     assert comp.engine.info()["ngroups"] == ngroups
+    assert comp.engine.info()["fwd_tensor_core"] == 0
+
+
+@pytest.mark.parametrize("shape", [(40, 256, 128, 64, 6), (16, 96, 64, 24, 5), (8, 32, 32, 8, 3), (40, 800, 512, 64, 4),
+                                   (40, 800, 512, 32, 4)])
+def test_tensor_core_forward(klb, oracle_blas, shape, monkeypatch):
+    """The tcgen05 forward time loop (num_stream <= 64, cell/recur dims multiples of 32) against the oracle, with the
+    activation record checked, and against the FP32 FFMA forward kernel on the same inputs."""
+    import torch
+    from parity_util import run_pair
+    I, C, R, S, T = shape
+    _, comp, _ = run_pair(klb, oracle_blas, I=I, C=C, R=R, S=S, T=T, nchunks=3, scale=0.08, seed=40 + S,
+                          check_record=True, init_state=True,
+                          resets=[None, (np.arange(S) % 2 == 0).astype(np.int32), None])
+    assert comp.engine.info()["fwd_tensor_core"] == 1
+    x = torch.randn(T * S, I, device="cuda")
+    a = comp.Copy()
+    monkeypatch.setenv("LSTMP_B200_TC_FWD", "0")
+    b = comp.Copy()
+    assert a.engine.info()["fwd_tensor_core"] == 1 and b.engine.info()["fwd_tensor_core"] == 0
+    oa, ob = a.Propagate(x), b.Propagate(x)
+    assert (oa - ob).abs().max().item() <= 2e-5 * ob.abs().max().item()
+    ra, rb = a.engine.get_record(False), b.engine.get_record(False)
+    assert np.abs(ra - rb).max() <= 2e-5 * np.abs(rb).max()
 
 
 def test_few_ctas(klb, oracle_mod, monkeypatch):
