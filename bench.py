@@ -369,7 +369,9 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
-    roofline = {"kernel": "lstmp_%s_kernel" % dom.split("_")[0], "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+    fwd_tc = bool(layers[0].engine.info().get("fwd_tensor_core"))
+    roofline = {"kernel": ("lstmp_fwd_tc_kernel" if fwd_tc else "lstmp_fwd_kernel") if dom == "fwd_recurrent"
+                else "lstmp_bwd_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                 "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None, "traffic": traffic,
                 "peak_source": peak_src, "alg_bytes_per_launch": ab, "alg_flops_per_launch": af,
                 "us_per_launch": dom_us, "achieved_tflops_fp32": af / (dom_us * 1e-6) / 1e12 if ach else None}
@@ -444,7 +446,7 @@ def main():
                                       "Update" % world if world > 1 else "1 GPU",
                        "l2": "inputs larger than L2: ring of %d distinct (feature, out_diff) chunks = %.0f MB" % (
                            ring, ring * bytes_per_chunk / 1e6),
-                       "decomposition": {k: info[k] for k in ("ngroups", "ctas_per_group", "streams_per_group",
+                       "decomposition": {k: info[k] for k in ("fwd_tensor_core", "ngroups", "ctas_per_group", "streams_per_group",
                                                               "cells_per_cta", "rcols_per_cta", "gemm_backend")}},
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": sampler.summary(), "roofline": roofline,
             "chunk_roofline": chunk_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,

@@ -21,6 +21,7 @@
 //                K=8) x 12 per 32-deep K block and tcgen05.commit onto the stage's "empty"
 //                mbarrier / the accumulator-ready mbarrier.
 // 3-stage shared-memory ring, mbarrier full/empty handshakes, accumulator in TMEM.
+#include <cstdlib>
 #include "lstmp_common.cuh"
 #include "lstmp_kernels.h"
 #include "lstmp_tc.cuh"
@@ -30,13 +31,21 @@ namespace lstmp {
 namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;        // fp32 elements per stage along K (= 4 MMAs of K=8)
-constexpr int NSTAGE = 2;      // UMMA operand stages (hi/lo tiles of A and B)
 constexpr int NRAW = 3;        // K blocks of raw fp32 operands in flight per CTA (cp.async landing slots)
 constexpr int LOADERS = 256;  // warps 0-7
 constexpr int THREADS = LOADERS + 32;
 
 // operand tiles are SWIZZLE_128B K-major (lstmp_tc.cuh): rows x 128 bytes, dense
 __host__ __device__ constexpr uint32_t tile_bytes(int rows, bool) { return (uint32_t)rows * 128u; }
+
+// Global operand load that the compiler may not sink towards its use (register-prefetch variant).
+__device__ __forceinline__ float4 ldg_early(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
 
 // One operand's loader state.  The shared-memory tile is ALWAYS K-major (the layout validated on
 // hardware); a source stored with the M/N index contiguous ("MN-major", e.g. DGIFO^T for the weight
@@ -80,6 +89,34 @@ struct Loader {
           uint8_t* dst = raw + ((size_t)(blk * 4 + kk) * LOADERS + tid) * 16;
           if (b < NBLK && gr < nrows && gk < K) cp_async16(dst, src + (size_t)gk * ld + gr);
           else *reinterpret_cast<float4*>(dst) = z;  // row kk of the block: 4 consecutive mn at k = 4kc+kk
+        }
+      }
+    }
+  }
+  // Register-prefetch variant (STAGED = false): the same units straight into v[] with LDG.128; the caller rotates
+  // several Loader objects so that the loads of later K blocks are in flight.  Half the shared-memory traffic of the
+  // staged variant (no landing slot to write and read back).
+  __device__ __forceinline__ void load(const float* __restrict__ src, long long ld, int row0, int nrows, int k0,
+                                       int K, int tid) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!MN) {
+#pragma unroll
+      for (int i = 0; i < UNITS; ++i) {
+        const int u = tid + i * LOADERS;
+        const int kc = u % (BK / 4), r = u / (BK / 4);
+        const int gr = row0 + r, gk = k0 + 4 * kc;
+        v[i] = (gr < nrows && gk < K) ? ldg_early(src + (size_t)gr * ld + gk) : z;
+      }
+    } else {
+#pragma unroll
+      for (int blk = 0; blk < BPT; ++blk) {
+        const int b = tid + blk * LOADERS;
+        const int mb = b % (ROWS / 4), kc = b / (ROWS / 4);
+        const int gr = row0 + 4 * mb;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int gk = k0 + 4 * kc + kk;
+          v[blk * 4 + kk] = (b < NBLK && gr < nrows && gk < K) ? ldg_early(src + (size_t)gk * ld + gr) : z;
         }
       }
     }
@@ -143,27 +180,29 @@ struct Loader {
   }
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool STAGED>
 struct Smem {
+  static constexpr int NSTAGE = STAGED ? 2 : 3;                  // UMMA operand stages (hi/lo tiles of A and B)
   static constexpr uint32_t A_BYTES = tile_bytes(BM, false);
   static constexpr uint32_t B_BYTES = tile_bytes(BN, false);
   static constexpr uint32_t STAGE = 2 * A_BYTES + 2 * B_BYTES;  // A_hi | A_lo | B_hi | B_lo
   static constexpr uint32_t RAW_A = Loader<BM, A_MN>::RAW_BYTES, RAW_B = Loader<BN, B_MN>::RAW_BYTES;
   static constexpr uint32_t RAW = RAW_A + RAW_B;                 // one K block of raw fp32 operands
-  static constexpr uint32_t TOTAL = NSTAGE * STAGE + NRAW * RAW + 2048;  // + barriers / tmem slot + alignment slack
+  static constexpr uint32_t TOTAL = NSTAGE * STAGE + (STAGED ? NRAW * RAW : 0) + 2048;  // + barriers, alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool STAGED>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float alpha,
                const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float beta,
                const float* __restrict__ bias, int k_per_split, float* __restrict__ split_ws) {
-  using SM = Smem<BN, A_MN, B_MN>;
+  using SM = Smem<BN, A_MN, B_MN, STAGED>;
+  constexpr int NSTAGE = SM::NSTAGE;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // 1024-byte align the tile area (SWIZZLE_128B atoms)
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* raw = tiles + NSTAGE * SM::STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(raw + NRAW * SM::RAW);
+  uint64_t* full = reinterpret_cast<uint64_t*>(raw + (STAGED ? NRAW * SM::RAW : 0));
   uint64_t* empty = full + NSTAGE;
   uint64_t* accum_ready = empty + NSTAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
@@ -208,37 +247,69 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
 
   if (warp < 8) {
     // =============================== loader / transform ==================================
-    Loader<BM, A_MN> la;
-    Loader<BN, B_MN> lb;
-#pragma unroll
-    for (int i = 0; i < NRAW; ++i) {
-      if (i < nkb) {
-        la.issue(raw + i * SM::RAW, A, lda, m0, M, i * BK, K, tid);
-        lb.issue(raw + i * SM::RAW + SM::RAW_A, B, ldb, n0, N, i * BK, K, tid);
+    if constexpr (STAGED) {
+      Loader<BM, A_MN> la;
+      Loader<BN, B_MN> lb;
+  #pragma unroll
+      for (int i = 0; i < NRAW; ++i) {
+        if (i < nkb) {
+          la.issue(raw + i * SM::RAW, A, lda, m0, M, i * BK, K, tid);
+          lb.issue(raw + i * SM::RAW + SM::RAW_A, B, ldb, n0, N, i * BK, K, tid);
+        }
+        cp_async_commit();
       }
-      cp_async_commit();
-    }
-    int rs = 0;  // raw slot of K block kb
-    for (int kb = 0; kb < nkb; ++kb) {
-      cp_async_wait<NRAW - 1>();  // this thread's copies of K block kb have landed
-      uint8_t* rw = raw + rs * SM::RAW;
-      la.fetch(rw, tid);
-      lb.fetch(rw + SM::RAW_A, tid);
-      if (kb + NRAW < nkb) {
-        la.issue(rw, A, lda, m0, M, (kb + NRAW) * BK, K, tid);
-        lb.issue(rw + SM::RAW_A, B, ldb, n0, N, (kb + NRAW) * BK, K, tid);
+      int rs = 0;  // raw slot of K block kb
+      for (int kb = 0; kb < nkb; ++kb) {
+        cp_async_wait<NRAW - 1>();  // this thread's copies of K block kb have landed
+        uint8_t* rw = raw + rs * SM::RAW;
+        la.fetch(rw, tid);
+        lb.fetch(rw + SM::RAW_A, tid);
+        if (kb + NRAW < nkb) {
+          la.issue(rw, A, lda, m0, M, (kb + NRAW) * BK, K, tid);
+          lb.issue(rw + SM::RAW_A, B, ldb, n0, N, (kb + NRAW) * BK, K, tid);
+        }
+        cp_async_commit();  // one group per K block (possibly empty) keeps the wait_group arithmetic uniform
+        if (++rs == NRAW) rs = 0;
+        const int s = kb % NSTAGE;
+        if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
+        uint8_t* st = tiles + (size_t)s * SM::STAGE;
+        la.store(st, st + SM::A_BYTES, tid);
+        lb.store(st + 2 * SM::A_BYTES, st + 2 * SM::A_BYTES + SM::B_BYTES, tid);
+        // The proxy fence lives on the consumer side (MMA warp, after its acquire-wait): here it would compile to
+        // MEMBAR.ALL.CTA and wait for the copies of the next K blocks.  One arrival per warp.
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&full[s]);
       }
-      cp_async_commit();  // one group per K block (possibly empty) keeps the wait_group arithmetic uniform
-      if (++rs == NRAW) rs = 0;
-      const int s = kb % NSTAGE;
-      if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
-      uint8_t* st = tiles + (size_t)s * SM::STAGE;
-      la.store(st, st + SM::A_BYTES, tid);
-      lb.store(st + 2 * SM::A_BYTES, st + 2 * SM::A_BYTES + SM::B_BYTES, tid);
-      // The proxy fence lives on the consumer side (MMA warp, after its acquire-wait): here it would compile to
-      // MEMBAR.ALL.CTA and wait for the copies of the next K blocks.  One arrival per warp.
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&full[s]);
+    } else {
+      // Four register sets per operand: the global loads of K blocks kb+1 .. kb+3 are in flight while block kb is
+      // split and stored.
+      constexpr int PF = 4;
+      Loader<BM, A_MN> la0, la1, la2, la3;
+      Loader<BN, B_MN> lb0, lb1, lb2, lb3;
+      la0.load(A, lda, m0, M, 0, K, tid);
+      lb0.load(B, ldb, n0, N, 0, K, tid);
+      if (nkb > 1) { la1.load(A, lda, m0, M, BK, K, tid); lb1.load(B, ldb, n0, N, BK, K, tid); }
+      if (nkb > 2) { la2.load(A, lda, m0, M, 2 * BK, K, tid); lb2.load(B, ldb, n0, N, 2 * BK, K, tid); }
+      if (nkb > 3) { la3.load(A, lda, m0, M, 3 * BK, K, tid); lb3.load(B, ldb, n0, N, 3 * BK, K, tid); }
+      auto step = [&](Loader<BM, A_MN>& la, Loader<BN, B_MN>& lb, int kb) {
+        const int s = kb % NSTAGE;
+        if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
+        uint8_t* st = tiles + (size_t)s * SM::STAGE;
+        la.store(st, st + SM::A_BYTES, tid);
+        lb.store(st + 2 * SM::A_BYTES, st + 2 * SM::A_BYTES + SM::B_BYTES, tid);
+        if (kb + PF < nkb) {
+          la.load(A, lda, m0, M, (kb + PF) * BK, K, tid);
+          lb.load(B, ldb, n0, N, (kb + PF) * BK, K, tid);
+        }
+        __syncwarp();  // proxy fence on the consumer side; one arrival per warp
+        if ((tid & 31) == 0) mbar_arrive(&full[s]);
+      };
+      for (int kb = 0; kb < nkb; kb += PF) {
+        step(la0, lb0, kb);
+        if (kb + 1 < nkb) step(la1, lb1, kb + 1);
+        if (kb + 2 < nkb) step(la2, lb2, kb + 2);
+        if (kb + 3 < nkb) step(la3, lb3, kb + 3);
+      }
     }
     // =============================== epilogue ============================================
     mbar_wait(accum_ready, 0);
@@ -349,18 +420,18 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(float* __restrict__ 
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool STAGED>
 static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
                               long long lda, const float* B, long long ldb, float beta, const float* bias,
                               cudaStream_t stream, float* ws, size_t ws_floats, int* nlaunch) {
-  using SM = Smem<BN, A_MN, B_MN>;
+  using SM = Smem<BN, A_MN, B_MN, STAGED>;
   *nlaunch = 1;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (!attr_set[dev & 63]) {
-    e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<BN, A_MN, B_MN, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SM::TOTAL);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
@@ -379,7 +450,7 @@ static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, floa
     const int kbs = (nkb + splits - 1) / splits;        // K blocks per split
     splits = (nkb + kbs - 1) / kbs;                      // drop empty tail splits
     grid.z = splits;
-    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
+    gemm_tc_kernel<BN, A_MN, B_MN, STAGED><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
                                                                        bias, kbs * BK, ws);
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return e2;
@@ -389,7 +460,7 @@ static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, floa
     *nlaunch = 2;
     return cudaGetLastError();
   }
-  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
+  gemm_tc_kernel<BN, A_MN, B_MN, STAGED><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
                                                                      bias, 0, nullptr);
   return cudaGetLastError();
 }
@@ -414,8 +485,17 @@ cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float a
   if (!al16(C)) return cudaSuccess;
   *handled = true;
   const bool small_n = (N <= 64);
-#define LSTMP_TC_CASE(BN_, AMN_, BMN_) \
-  return tc::launch_one<BN_, AMN_, BMN_>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, ws_floats, nlaunch)
+  // operand loader variant: 1 = cp.async into raw landing slots (default; measured 43 vs 52 us on the weight-gradient
+  // GEMMs), 0 = LDG.128 into rotating register sets (LSTMP_B200_GEMM_STAGED=0)
+  static const bool staged = [] {
+    const char* v = getenv("LSTMP_B200_GEMM_STAGED");
+    return !(v && *v) || atoi(v) != 0;
+  }();
+#define LSTMP_TC_CASE(BN_, AMN_, BMN_)                                                                               \
+  return staged ? tc::launch_one<BN_, AMN_, BMN_, true>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, \
+                                                        ws, ws_floats, nlaunch)                                      \
+                : tc::launch_one<BN_, AMN_, BMN_, false>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, \
+                                                         ws, ws_floats, nlaunch)
   if (small_n) {
     if (!a_mn && !b_mn) LSTMP_TC_CASE(64, false, false);
     if (!a_mn && b_mn) LSTMP_TC_CASE(64, false, true);

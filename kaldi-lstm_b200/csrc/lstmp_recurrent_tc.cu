@@ -9,14 +9,15 @@
 //
 //   A = the all-gathered activations of ALL streams (r(t-1) for the gates, m(t) for the projection), rows 0..S-1
 //       the "hi" halves (x & 0xffffe000, exact TF32) and rows S..2S-1 the "lo" halves (x - hi), written by 8
-//       loader warps (ld.global.cg from L2 -> split -> st.shared in the UMMA K-major layout) into a ring of
-//       [128 rows x 32 k] slots guarded by full/empty mbarriers;
+//       loader warps (cp.async.cg from L2 -> landing slot -> split -> st.shared in the SWIZZLE_128B K-major layout)
+//       into a ring of [128 rows x 32 k] slots guarded by full/ready/empty mbarriers;
 //   B = the CTA's stationary weight slice, hi rows then lo rows, split ONCE per launch.
 //
 // One MMA therefore yields all four hi/lo cross products: result[s][n] = D[s][n] + D[s][nh+n] + D[S+s][n] +
-// D[S+s][nh+n] (the lo*lo term costs nothing extra).  Per MMA the tensor pipe needs N/2 cycles (N = 48 for the gates
-// of 6 cells, 16 for 4 projection columns) -- the products take ~2.3 k cycles per timestep instead of ~30 k of FFMA,
-// and the step is bounded by the L2 all-gather (328 KB per CTA and step) and the two group barriers.
+// D[S+s][nh+n] (the lo*lo term costs nothing extra).  Per MMA the tensor pipe needs max(N/2, ~40) cycles (N = 48 for
+// the gates of 6 cells, 16 for 4 projection columns).  Measured: 367 us per launch vs 423 us for the
+// FFMA kernel; a chunk of 32 k still takes ~600 cycles, far above what L2 (55-72 B/clk/SM) and the MMAs (180 cycles)
+// need -- see the experiment log for what was ruled out.
 #include "lstmp_common.cuh"
 #include "lstmp_kernels.h"
 #include "lstmp_tc.cuh"
@@ -27,7 +28,8 @@ namespace tcf {
 constexpr int KC = 32;                          // k per ring slot (4 MMAs of K = 8)
 constexpr int SLABS = KC / 4;                   // 16-byte K slabs per slot
 constexpr int LOADERS = 256;                    // warps 0-7
-constexpr int PF = 5;                           // chunks of cp.async copies each loader thread keeps in flight
+constexpr int PF = 3;                           // STAGED: chunks of cp.async copies each loader thread keeps in flight
+constexpr int PFR = 4;                          // !STAGED: chunks of LDG.128 (register sets) in flight per loader thread
 constexpr uint32_t SLOT_BYTES = 128 * 128;      // activation slot: 128 rows x 128 B, SWIZZLE_128B (lstmp_tc.cuh)
 constexpr int MAX_SLOTS = 8;
 constexpr uint32_t TMEM_COLS = 512;             // the whole TMEM: this CTA is alone on its SM
@@ -52,6 +54,7 @@ __device__ __forceinline__ void split4(float4 x, float4& h, float4& l) {
 // red[row*ldred + n] = D[row][n] + D[row][nh + n]  for the 128 stacked rows, n < nvalid.
 // X: [S x K] activations in global memory (row stride ld), written by other CTAs before the preceding group barrier.
 // Every thread of the CTA calls this; contains one __syncthreads.
+template <bool STAGED>
 __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const float* __restrict__ X, int ld, int K,
                                            uint32_t b_addr, uint32_t chunk_b, uint32_t idesc, uint32_t tmem_d, int nh,
                                            int nvalid, uint8_t* ring, uint64_t* full, uint64_t* ready,
@@ -69,11 +72,9 @@ __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const
 
   if (warp < 8) {
     // ------------------------------ loader / transform ---------------------------------------
-    // Stage 1: cp.async.cg (LDGSTS, L2 -> raw staging slots, PF chunks in flight per thread, tracked by cp.async
-    // groups).  Register prefetch (LDG into a rotating register set) was 5x slower: with 12 loads in flight per thread
-    // the 6 hardware scoreboards are shared, so waiting for the oldest load also waited for the newest one and every
-    // chunk paid a full L2 round trip (~780 cycles).
-    // Stage 2: each thread reads back ITS OWN two 16-byte units, splits them and stores hi / lo into the UMMA tile.
+    // STAGED (default): stage 1 = cp.async.cg (LDGSTS, L2 -> raw landing slots, PF chunks in flight per thread,
+    // tracked by cp.async groups); stage 2 = each thread reads back ITS OWN two 16-byte units, splits them and stores
+    // hi / lo into the UMMA tile.  The register-prefetch variant below measured 10 % slower (405 vs 367 us).
     const int S = p.S;
     const int nunits = S * SLABS;  // float4 units per chunk (<= 512)
     const int u0 = tid, u1 = tid + LOADERS;
@@ -83,52 +84,102 @@ __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const
     const float* g1 = X + (size_t)r1 * ld + 4 * kc;
     // hi row r -> tile row r, lo row r -> tile row S + r (S % 8 == 0: same swizzle phase, offset S*128 bytes)
     const uint32_t so0 = tc::sw128_off(r0, kc), so1 = tc::sw128_off(r1, kc), lo_off = (uint32_t)S * 128;
-    uint8_t* my0 = stage + (size_t)u0 * 16;
-    uint8_t* my1 = stage + (size_t)u1 * 16;
-    const size_t stage_bytes = (size_t)nunits * 16;
-    auto issue = [&](int c, int st) {
-      const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
-      if (ok0) cp_async16(my0 + st * stage_bytes, g0 + ce * KC);
-      if (ok1) cp_async16(my1 + st * stage_bytes, g1 + ce * KC);
-    };
-#pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      if (i < nch) issue(i, i);
-      cp_async_commit();
-    }
-    for (int c0 = 0; c0 < nch; c0 += PF) {
-#pragma unroll
+    if constexpr (STAGED) {
+      uint8_t* my0 = stage + (size_t)u0 * 16;
+      uint8_t* my1 = stage + (size_t)u1 * 16;
+      const size_t stage_bytes = (size_t)nunits * 16;
+      auto issue = [&](int c, int st) {
+        const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
+        if (ok0) cp_async16(my0 + st * stage_bytes, g0 + ce * KC);
+        if (ok1) cp_async16(my1 + st * stage_bytes, g1 + ce * KC);
+      };
+  #pragma unroll
       for (int i = 0; i < PF; ++i) {
-        const int c = c0 + i;
-        if (c < nch) {
-          cp_async_wait<PF - 1>();  // this thread's copies of chunk c have landed
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 x0 = ok0 ? *reinterpret_cast<const float4*>(my0 + i * stage_bytes) : z;
-          const float4 x1 = ok1 ? *reinterpret_cast<const float4*>(my1 + i * stage_bytes) : z;
-          if (c + PF < nch) issue(c + PF, i);
-          cp_async_commit();  // one group per iteration (possibly empty) keeps the wait_group arithmetic uniform
-          if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
-          uint8_t* st = ring + (size_t)slot * SLOT_BYTES;
-          float4 h, l;
-          if (ok0) {
-            split4(x0, h, l);
-            *reinterpret_cast<float4*>(st + so0) = h;
-            *reinterpret_cast<float4*>(st + so0 + lo_off) = l;
+        if (i < nch) issue(i, i);
+        cp_async_commit();
+      }
+      for (int c0 = 0; c0 < nch; c0 += PF) {
+  #pragma unroll
+        for (int i = 0; i < PF; ++i) {
+          const int c = c0 + i;
+          if (c < nch) {
+            cp_async_wait<PF - 1>();  // this thread's copies of chunk c have landed
+          stamp(50);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 x0 = ok0 ? *reinterpret_cast<const float4*>(my0 + i * stage_bytes) : z;
+            const float4 x1 = ok1 ? *reinterpret_cast<const float4*>(my1 + i * stage_bytes) : z;
+            if (c + PF < nch) issue(c + PF, i);
+            cp_async_commit();  // one group per iteration (possibly empty) keeps the wait_group arithmetic uniform
+            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+            uint8_t* st = ring + (size_t)slot * SLOT_BYTES;
+            float4 h, l;
+            if (ok0) {
+              split4(x0, h, l);
+              *reinterpret_cast<float4*>(st + so0) = h;
+              *reinterpret_cast<float4*>(st + so0 + lo_off) = l;
+            }
+            if (ok1) {
+              split4(x1, h, l);
+              *reinterpret_cast<float4*>(st + so1) = h;
+              *reinterpret_cast<float4*>(st + so1 + lo_off) = l;
+            }
+            // The proxy fence is on the consumer side (issuer warp, after its acquire-wait): fence.proxy.async is
+            // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS.  The release-arrive orders the stores.
+            // ONE arrival per warp: 256 per-thread arrivals on the same mbarrier serialise (~3 cycles each) and were the
+            // whole cost of a chunk (~800 cycles).  __syncwarp orders the other lanes' stores before lane 0's release.
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[slot]);
+            if (++slot == (uint32_t)nslot) {
+              slot = 0;
+              ++use;
+            }
           }
-          if (ok1) {
-            split4(x1, h, l);
-            *reinterpret_cast<float4*>(st + so1) = h;
-            *reinterpret_cast<float4*>(st + so1 + lo_off) = l;
-          }
-          // The proxy fence is on the consumer side (issuer warp, after its acquire-wait): fence.proxy.async is
-          // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS.  The release-arrive orders the stores.
-          // ONE arrival per warp: 256 per-thread arrivals on the same mbarrier serialise (~3 cycles each) and were the
-          // whole cost of a chunk (~800 cycles).  __syncwarp orders the other lanes' stores before lane 0's release.
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&full[slot]);
-          if (++slot == (uint32_t)nslot) {
-            slot = 0;
-            ++use;
+        }
+      }
+    } else {
+      // Register prefetch (LSTMP_B200_TC_STAGED=0): PFR chunks of LDG.128 (ld.global.cg) in flight per thread, no
+      // landing slots -- a third less shared-memory traffic per chunk and room for a 6-slot ring, yet slower.
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v[PFR][2];
+#pragma unroll
+      for (int i = 0; i < PFR; ++i) {
+        v[i][0] = z;
+        v[i][1] = z;
+        if (i < nch) {
+          const int ce = (i + rot < nch) ? i + rot : i + rot - nch;
+          if (ok0) v[i][0] = ld_cg_f4(g0 + ce * KC);
+          if (ok1) v[i][1] = ld_cg_f4(g1 + ce * KC);
+        }
+      }
+      for (int c0 = 0; c0 < nch; c0 += PFR) {
+#pragma unroll
+        for (int i = 0; i < PFR; ++i) {
+          const int c = c0 + i;
+          if (c < nch) {
+            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+            uint8_t* st = ring + (size_t)slot * SLOT_BYTES;
+            float4 h, l;
+            if (ok0) {
+              split4(v[i][0], h, l);
+              *reinterpret_cast<float4*>(st + so0) = h;
+              *reinterpret_cast<float4*>(st + so0 + lo_off) = l;
+            }
+            if (ok1) {
+              split4(v[i][1], h, l);
+              *reinterpret_cast<float4*>(st + so1) = h;
+              *reinterpret_cast<float4*>(st + so1 + lo_off) = l;
+            }
+            if (c + PFR < nch) {
+              const int ce = (c + PFR + rot < nch) ? c + PFR + rot : c + PFR + rot - nch;
+              if (ok0) v[i][0] = ld_cg_f4(g0 + ce * KC);
+              if (ok1) v[i][1] = ld_cg_f4(g1 + ce * KC);
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[slot]);
+            if (++slot == (uint32_t)nslot) {
+              slot = 0;
+              ++use;
+            }
           }
         }
       }
@@ -136,6 +187,7 @@ __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const
     if (warp < 4) {
       // ---------------------------- accumulator -> shared memory ------------------------------
       mbar_wait(accum, ps.acc & 1);
+      stamp(53);
       tc::tc_fence_after();
       const int row = warp * 32 + lane;  // TMEM lane = stacked activation row
       const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
@@ -202,6 +254,7 @@ __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const
 }
 }  // namespace tcf
 
+template <bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using namespace tcf;
   extern __shared__ __align__(16) uint8_t smem_raw_tc[];
@@ -320,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_
       // r_{t-1}: carried state for the first frame of the chunk, else rbuf block tt
       const float* X = (tt == 0) ? p.state_r : p.rbuf + (size_t)tt * S * R;
       // gifo(t) += r(t-1) * W_gifo_r^T                                       (LPS.h:275)
-      tc_product(p, ps, X, R, R, bg_s, p.chunk_g, idesc_g, tmem_base + COL_G, 4 * cpc, 4 * nc, ring, full, ready, empty, accum,
+      tc_product<STAGED>(p, ps, X, R, R, bg_s, p.chunk_g, idesc_g, tmem_base + COL_G, 4 * cpc, 4 * nc, ring, full, ready, empty, accum,
                  red, stage);
       stamp(11);
       for (int idx = tid; idx < S * nc; idx += kThreads) {
@@ -363,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_
     stamp(21);
     // ================= phase 2: projection r(t) = m(t) * W_r_m^T for my columns (LPS.h:312) ==
     if (nr > 0) {
-      tc_product(p, ps, p.mbuf + (size_t)tt * S * C, C, C, bp_s, p.chunk_p, idesc_p, tmem_base + COL_P, rpc, nr, ring,
+      tc_product<STAGED>(p, ps, p.mbuf + (size_t)tt * S * C, C, C, bp_s, p.chunk_p, idesc_p, tmem_base + COL_P, rpc, nr, ring,
                  full, ready, empty, accum, red, stage);
       stamp(22);
       for (int idx = tid; idx < S * nr; idx += kThreads) {
@@ -397,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTcParams* p, size_t* smem_bytes) {
+bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int staged, FwdTcParams* p, size_t* smem_bytes) {
   using namespace tcf;
   if (S < 8 || S > 64 || (S & 7)) return false;  // A tile: 2*S stacked rows <= 128 = the MMA's M; lo rows at row S
   if (C % KC || R % KC || nctas < 1) return false;
@@ -424,7 +477,8 @@ bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTcParams*
   p->off_ring = (unsigned)off;
   const int ldred = ((4 * cpc > rpc ? 4 * cpc : rpc) | 1);
   p->ldred = (unsigned)ldred;
-  const size_t stage_total = (size_t)PF * S * SLABS * 16;
+  p->staged = staged;
+  const size_t stage_total = staged ? (size_t)PF * S * SLABS * 16 : 0;
   const size_t tail = ((stage_total + 1023) & ~size_t(1023)) + (((size_t)S * cpc * 4 + 1023) & ~size_t(1023)) +
                       1024 /* peepholes */ + 1024 /* barriers + tmem slot */;
   const size_t reserve = 1024 /* base alignment */ + (size_t)static_smem_reserve();
@@ -445,14 +499,18 @@ bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTcParams*
 }
 
 cudaError_t fwd_tc_set_smem_limit(size_t bytes) {
-  return cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)bytes);
 }
 
 cudaError_t launch_fwd_tc(const FwdTcParams& p, size_t smem_bytes, cudaStream_t stream) {
   void* args[] = {(void*)&p};
   dim3 grid(p.nctas), block(kThreads);
-  return cudaLaunchCooperativeKernel((const void*)lstmp_fwd_tc_kernel, grid, block, args, smem_bytes, stream);
+  const void* fn = p.staged ? (const void*)lstmp_fwd_tc_kernel<true> : (const void*)lstmp_fwd_tc_kernel<false>;
+  return cudaLaunchCooperativeKernel(fn, grid, block, args, smem_bytes, stream);
 }
 
 }  // namespace lstmp

@@ -96,7 +96,7 @@ def full_selected(rnd, rep):
     acc = collections.defaultdict(list)
     for r in data:
         name = r[col["Kernel Name"]]
-        key = ("fwd_recurrent" if "lstmp_fwd_kernel" in name else "bwd_recurrent" if "lstmp_bwd_kernel" in name
+        key = ("fwd_recurrent" if ("lstmp_fwd_kernel" in name or "lstmp_fwd_tc_kernel" in name) else "bwd_recurrent" if "lstmp_bwd_kernel" in name
                else "gemm_tc" if "gemm_tc_kernel" in name else None)
         if key is None:
             continue
