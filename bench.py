@@ -188,18 +188,102 @@ def run_reference_arm(args, wl):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def bench_xent(args):
+    """masked cross-entropy with sparse targets at the cfg 4 per-GPU chunk
+    (S=32 x T=20 = 640 frames x 16624 pdfs).  One step = one EvalMasked call (CSR posterior H2D + row kernel +
+    fixed-order reduction); metric frames/s; HBM-bound: 8 bytes per (frame, pdf)."""
+    import numpy as np
+    rows, P = 640, 16624
+    cfg = {"workload": "xent-cfg4: Xent::EvalMasked, 640 frames (S=32 x T=20) x 16624 pdfs, hard labels, 1/5 masked",
+           "l2": "ring of 16 distinct net_out matrices = 681 MB > L2"}
+    from oracle import xent_oracle
+    if args.impl == "reference":
+        mask, y, post = xent_oracle.random_case(rows, P, seed=1, mask_every=5)
+        o = xent_oracle.XentOracle()
+        for _ in range(args.warmup):
+            o.eval_masked(mask, y, post)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            o.eval_masked(mask, y, post)
+        dt = time.perf_counter() - t0
+        v = rows * args.steps / dt
+        print(json.dumps({"impl": "reference", "metric": "frames/sec Xent::EvalMasked", "value": v, "unit": "frames/s",
+                          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": 1, "kind": "port",
+                                           "sample": "%d dense EvalMasked calls (numpy restatement)" % args.steps},
+                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+    import torch
+    import kaldi_lstm_b200 as klb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no GPU visible; the product has no CPU path (use --impl reference for the CPU arm)")
+    nring = 16
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ys = [torch.softmax(torch.randn(rows, P, device="cuda", generator=g) * 2, dim=1) for _ in range(nring)]
+    diff = torch.empty(rows, P, device="cuda")
+    rng = np.random.RandomState(2)
+    post = (np.arange(rows + 1, dtype=np.int32), rng.randint(0, P, rows).astype(np.int32), np.ones(rows, np.float32))
+    mask = (np.arange(rows) % 5 != 0).astype(np.float32)
+    x = klb.Xent(rows)
+    for i in range(max(args.warmup, 3)):
+        x.EvalMasked(mask, ys[i % nring], post, diff)
+    torch.cuda.synchronize()
+    l0 = x.Stats()["kernel_launches"]
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(args.steps):
+        x.EvalMasked(mask, ys[i % nring], post, diff)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    launches = x.Stats()["kernel_launches"] - l0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    alg = 8.0 * rows * P
+    ach = alg / (ms / args.steps * 1e-3) / 1e9
+    o = xent_oracle.XentOracle()
+    m2, y2, p2 = xent_oracle.random_case(rows, P, seed=1, mask_every=5)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < min(args.cpu_seconds, 10.0):
+        o.eval_masked(m2, y2, p2)
+        n += 1
+    dt = time.perf_counter() - t0
+    print(json.dumps({"metric": "frames/sec Xent::EvalMasked", "value": rows * args.steps / (ms * 1e-3), "unit": "frames/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": cfg, "gpu_launches": int(launches),
+                      "e2e": {"value": rows * args.steps / (ms * 1e-3), "unit": "frames/s",
+                              "h2d_bytes_per_step": int(4 * (rows + 1) + 12 * rows), "d2h_bytes_per_step": 0,
+                              "what": "the timed call already takes the host posterior / mask and copies them"},
+                      "roofline": {"kernel": "xent_rows_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                                   "frac": ach / hbm, "traffic": None, "alg_bytes_per_launch": alg,
+                                   "note": "whole-call time (H2D of the CSR posterior + 2 kernels), not the kernel alone"},
+                      "cpu_baseline": {"value": rows * n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+                                       "sample": "%d dense EvalMasked calls (numpy restatement of nnet-loss.cc:76-164)" % n}}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["xent-cfg4"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra cfg2 (NumStream=4) measurement")
     args = ap.parse_args()
+    if args.workload == "xent-cfg4":
+        return bench_xent(args)
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

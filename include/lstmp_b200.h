@@ -164,6 +164,33 @@ int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, int N, int K
                           size_t lda, int tA, const float* B, size_t ldb, int tB, float beta, const float* bias,
                           void* stream);
 
+/* ---- Masked cross-entropy with sparse targets --------------------------------
+ * Replaces Xent::EvalMasked (google/nnet/nnet-loss.cc:76-164) and the accumulators / Report() of class Xent
+ * (nnet-loss.h:33-75, nnet-loss.cc:293-307).  net_out = the softmax outputs [num_frames x num_pdf] (device, row
+ * stride ld_out), diff [num_frames x num_pdf] (device, fully written) = frame_mask * (net_out - target).  The Kaldi
+ * `Posterior` (host std::vector<std::vector<std::pair<int32,BaseFloat>>>) is passed flattened as CSR:
+ * post_row_ptr[num_frames + 1], post_pdf[nnz], post_weight[nnz] (host; duplicates of a pdf within a frame accumulate,
+ * nnet-loss.cc:94); frame_mask is the host Vector of 0/1 floats (nnet-loss.cc:76, :98-100).  A pdf-id outside
+ * [0, num_pdf) is the reference's KALDI_ERR (:88-91) -> LSTMP_B200_EINVAL.  Statistics accumulate on the device
+ * (loss_, entropy_ in double; correct_, frames_) and are read back only by lstmp_b200_xent_get_stats.
+ * The call is asynchronous on `stream`; the host arrays may be reused as soon as it returns. */
+typedef struct lstmp_b200_xent* lstmp_b200_xent_handle_t;
+typedef struct {
+  double loss;      /* loss_    : -sum mask * t * log(y)                 (nnet-loss.cc:127-131,141) */
+  double entropy;   /* entropy_ : -sum mask * t * log(t + 1e-20)         (:134-139,142) */
+  long long correct;/* correct_ : valid frames whose arg-max matches the target's      (:109-124,143) */
+  long long frames; /* frames_  : sum over calls of (int32) sum(frame_mask)            (:144-145) */
+  unsigned long long kernel_launches;
+} lstmp_b200_xent_stats_t;
+int lstmp_b200_xent_create(int max_frames, int device, lstmp_b200_xent_handle_t* out);
+int lstmp_b200_xent_destroy(lstmp_b200_xent_handle_t h);
+int lstmp_b200_xent_eval_masked(lstmp_b200_xent_handle_t h, const float* frame_mask_host, const float* net_out,
+                                size_t ld_out, int num_frames, int num_pdf, const int32_t* post_row_ptr_host,
+                                const int32_t* post_pdf_host, const float* post_weight_host, float* diff,
+                                size_t ld_diff, void* stream);
+int lstmp_b200_xent_get_stats(lstmp_b200_xent_handle_t h, lstmp_b200_xent_stats_t* out, void* stream);
+int lstmp_b200_xent_reset_stats(lstmp_b200_xent_handle_t h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

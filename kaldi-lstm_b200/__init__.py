@@ -10,7 +10,8 @@ google/nnet/bd-nnet-lstm-projected-streams.h) and of the trainer's multi-stream 
 There is no CPU fallback: importing works anywhere, but creating an engine without the built
 library or without a B200 raises.
 """
-from .engine import Engine, EngineError, lib_path, load_library  # noqa: F401
+from .engine import Engine, EngineError, XentEngine, lib_path, load_library  # noqa: F401
 from .component import LstmProjectedStreams, NnetTrainOptions  # noqa: F401
 from .dispatch import StreamDispatcher  # noqa: F401
+from .loss import Xent, posterior_to_csr  # noqa: F401
 from . import parallel  # noqa: F401

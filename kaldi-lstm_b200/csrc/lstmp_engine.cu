@@ -137,6 +137,9 @@ static bool make_decomp(int C, int R, int S, int sm_count, size_t smem_limit, in
 
 extern "C" int lstmp_b200_abi_version(void) { return 1; }
 extern "C" const char* lstmp_b200_last_error(void) { return g_err.c_str(); }
+namespace lstmp {
+void set_last_error(const char* msg) { g_err = msg ? msg : ""; }  // for the other translation units (lstmp_xent.cu)
+}
 
 static int alloc_f(float** p, size_t n, size_t* total) {
   cudaError_t e = cudaMalloc((void**)p, n * sizeof(float));

@@ -15,6 +15,8 @@ ABI_SYMBOLS = [
     "lstmp_b200_set_state", "lstmp_b200_reset", "lstmp_b200_propagate", "lstmp_b200_backpropagate",
     "lstmp_b200_update", "lstmp_b200_allreduce_grads_nccl", "lstmp_b200_get_info", "lstmp_b200_get_record",
     "lstmp_b200_timing_enable", "lstmp_b200_timing_read", "lstmp_b200_debug_gemm",
+    "lstmp_b200_xent_create", "lstmp_b200_xent_destroy", "lstmp_b200_xent_eval_masked",
+    "lstmp_b200_xent_get_stats", "lstmp_b200_xent_reset_stats",
 ]
 
 TIMING_KINDS = ["input_gemm", "fwd_recurrent", "bwd_recurrent", "in_diff_gemm", "wgrad_gemms", "small_grads",
@@ -37,6 +39,11 @@ class Info(ctypes.Structure):
         ("workspace_bytes", ctypes.c_size_t), ("kernel_launches", ctypes.c_ulonglong),
         ("gemm_backend", ctypes.c_int), ("weights_streamed", ctypes.c_int), ("fwd_tensor_core", ctypes.c_int),
     ]
+
+
+class XentStats(ctypes.Structure):
+    _fields_ = [("loss", ctypes.c_double), ("entropy", ctypes.c_double), ("correct", ctypes.c_longlong),
+                ("frames", ctypes.c_longlong), ("kernel_launches", ctypes.c_ulonglong)]
 
 
 class Timing(ctypes.Structure):
@@ -81,6 +88,11 @@ def load_library():
     L.lstmp_b200_debug_gemm.argtypes = [ci, vp, sz, ci, ci, ci, fp, vp, sz, ci, vp, sz, ci, fp, vp, vp]
     L.lstmp_b200_timing_enable.argtypes = [vp, ci]
     L.lstmp_b200_timing_read.argtypes = [vp, ctypes.POINTER(Timing)]
+    L.lstmp_b200_xent_create.argtypes = [ci, ci, ctypes.POINTER(vp)]
+    L.lstmp_b200_xent_destroy.argtypes = [vp]
+    L.lstmp_b200_xent_eval_masked.argtypes = [vp, vp, vp, sz, ci, ci, vp, vp, vp, vp, sz, vp]
+    L.lstmp_b200_xent_get_stats.argtypes = [vp, ctypes.POINTER(XentStats), vp]
+    L.lstmp_b200_xent_reset_stats.argtypes = [vp, vp]
     for name in ABI_SYMBOLS:
         f = getattr(L, name)
         if name not in ("lstmp_b200_last_error",):
@@ -251,3 +263,53 @@ def debug_gemm(backend, C, M, N, K, alpha, A, tA, B, tB, beta=0.0, bias=None):
                                  ctypes.c_void_p(A.data_ptr()), A.stride(0), int(tA), ctypes.c_void_p(B.data_ptr()),
                                  B.stride(0), int(tB), float(beta),
                                  ctypes.c_void_p(bias.data_ptr()) if bias is not None else None, st))
+
+
+class XentEngine:
+    """Device side of the masked cross-entropy with sparse targets (lstmp_b200_xent_*)."""
+
+    def __init__(self, max_frames, device=0):
+        L = load_library()
+        h = ctypes.c_void_p()
+        _chk(L.lstmp_b200_xent_create(int(max_frames), device, ctypes.byref(h)))
+        self._h = h
+        self.max_frames, self.device = int(max_frames), device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().lstmp_b200_xent_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval_masked(self, frame_mask_host, net_out, row_ptr, pdf, weight, diff):
+        """frame_mask_host / row_ptr / pdf / weight: host numpy arrays (CSR posterior); net_out, diff: CUDA tensors."""
+        import numpy as np
+        rows, num_pdf = net_out.shape
+        mask = np.ascontiguousarray(frame_mask_host, np.float32)
+        rp = np.ascontiguousarray(row_ptr, np.int32)
+        pd = np.ascontiguousarray(pdf, np.int32)
+        wt = np.ascontiguousarray(weight, np.float32)
+        if mask.size != rows or rp.size != rows + 1 or pd.size != wt.size:
+            raise EngineError(EINVAL, "mask / posterior sizes do not match the %d frames of net_out" % rows)
+        po, ldo = Engine._mat(net_out, num_pdf, "net_out")
+        pdiff, ldd = Engine._mat(diff, num_pdf, "diff")
+        if diff.shape[0] != rows:
+            raise EngineError(EINVAL, "diff rows != net_out rows")
+        _chk(load_library().lstmp_b200_xent_eval_masked(
+            self._h, ctypes.c_void_p(mask.ctypes.data), po, ldo, rows, num_pdf, ctypes.c_void_p(rp.ctypes.data),
+            ctypes.c_void_p(pd.ctypes.data) if pd.size else None, ctypes.c_void_p(wt.ctypes.data) if wt.size else None,
+            pdiff, ldd, Engine._stream()))
+
+    def stats(self):
+        st = XentStats()
+        _chk(load_library().lstmp_b200_xent_get_stats(self._h, ctypes.byref(st), Engine._stream()))
+        return {"loss": st.loss, "entropy": st.entropy, "correct": int(st.correct), "frames": int(st.frames),
+                "kernel_launches": int(st.kernel_launches)}
+
+    def reset_stats(self):
+        _chk(load_library().lstmp_b200_xent_reset_stats(self._h, Engine._stream()))

@@ -21,6 +21,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace kaldi {
@@ -122,6 +123,12 @@ class Vector {
  private:
   std::vector<Real> d_;
 };
+
+// upstream Vector derives from VectorBase; the compat surface needs only the read accessors
+template <class Real>
+using VectorBase = Vector<Real>;
+// hmm/posterior.h upstream
+typedef std::vector<std::vector<std::pair<int32, BaseFloat> > > Posterior;
 
 template <class Real>
 class Matrix {

@@ -31,3 +31,14 @@ def test_cpp_component_parity_on_gpu():
     r = subprocess.run([BIN, ORACLE], capture_output=True, text=True, timeout=120)
     print(r.stdout, r.stderr)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_xent_mirror_on_gpu():
+    """kaldi-lstm_b200/kaldi/b200-nnet-loss.h (B200Xent::EvalMasked / Report) against a dense host restatement."""
+    _build()
+    xbin = os.path.join(ROOT, "tests", "cpp", "_build", "xent_test")
+    r = subprocess.run([xbin], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
