@@ -14,4 +14,4 @@ from .engine import Engine, EngineError, XentEngine, lib_path, load_library  # n
 from .component import LstmProjectedStreams, NnetTrainOptions  # noqa: F401
 from .dispatch import StreamDispatcher  # noqa: F401
 from .loss import Xent, posterior_to_csr  # noqa: F401
-from . import parallel  # noqa: F401
+from . import nnet_io, parallel  # noqa: F401

@@ -9,6 +9,7 @@ forwards calls.  Matrices are torch CUDA float32 tensors standing in for CuMatri
 """
 import numpy as np
 
+from . import nnet_io
 from .engine import Engine, EngineError, EINVAL
 
 
@@ -102,6 +103,26 @@ class LstmProjectedStreams:
         other._engine.set_flat(1, self._engine.get_flat(1))
         other._engine.set_state(*self._engine.get_state())
         return other
+
+    # ---- model files (text form of ReadData / WriteData, LPS.h:101-150) ---------------------------------
+    def ToNnetComponent(self):
+        """This layer as an nnet_io.NnetComponent `<LstmProjectedStreams> out in <CellDim> C <NumStream> S [...]`."""
+        return nnet_io.lstm_component_from_flat(self.GetParams(), self.output_dim_, self.input_dim_, self.ncell_,
+                                                num_stream=self.nstream_)
+
+    @classmethod
+    def FromNnetComponent(cls, comp, device=0, max_frames=20, num_stream=None):
+        """Builds the layer from a parsed `<LstmProjectedStreams>` component, or from the standard version's
+        `<LstmProjected>` (standard/nnet/nnet-lstm-projected.h:111-123 -- same seven blocks, no <NumStream>), which runs
+        as the num_stream = 1 case of the streams engine unless `num_stream` says otherwise."""
+        if comp.type not in nnet_io.LSTM_TYPES:
+            raise RuntimeError("not an LSTM component: %s" % comp.type)
+        c = cls(comp.input_dim, comp.output_dim, device, max_frames)
+        c.ncell_ = int(comp.attr("<CellDim>"))
+        c.nstream_ = int(num_stream or comp.attr("<NumStream>") or 1)
+        c._make_engine()
+        c.SetParams(nnet_io.lstm_flat_params(comp))
+        return c
 
     def NumParams(self):
         return self._engine.num_params  # LPS.h:152-160

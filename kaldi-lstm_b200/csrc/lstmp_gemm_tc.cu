@@ -200,7 +200,15 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
   constexpr int NSTAGE = SM::NSTAGE;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // 1024-byte align the tile area (SWIZZLE_128B atoms)
+#ifdef LSTMP_TC_SHARED_SPACE
+  // Pointer arithmetic on the __shared__ array keeps the address space visible to the compiler: the loaders' accesses
+  // become STS.128 / LDS.128.  (Found at the end of round 1 by reading the SASS: with the integer round trip below
+  // every shared-memory access of this kernel is a GENERIC LD.E.128 / ST.E.128.  Not yet validated on hardware, hence
+  // opt-in: `make sts` builds _lib/liblstmp_b200_sts.so, select it with LSTMP_B200_LIB.)
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#else
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+#endif
   uint8_t* raw = tiles + NSTAGE * SM::STAGE;
   uint64_t* full = reinterpret_cast<uint64_t*>(raw + (STAGED ? NRAW * SM::RAW : 0));
   uint64_t* empty = full + NSTAGE;

@@ -258,7 +258,12 @@ template <bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using namespace tcf;
   extern __shared__ __align__(16) uint8_t smem_raw_tc[];
+#ifdef LSTMP_TC_SHARED_SPACE
+  // see lstmp_gemm_tc.cu: keeps the shared address space visible (STS/LDS instead of generic ST.E/LD.E); opt-in build
+  uint8_t* base = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);
+#else
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+#endif
   uint8_t* bg = base + p.off_bg;      // gate weight slice:   R/32 tiles of [roundup8(8*cpc) rows][128 B]  (hi rows, then lo)
   uint8_t* bp = base + p.off_bp;      // projection slice:    C/32 tiles of [roundup8(2*rpc) rows][128 B]
   uint8_t* ring = base + p.off_ring;  // nslot x [128 rows][128 B]

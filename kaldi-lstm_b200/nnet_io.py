@@ -1,0 +1,204 @@
+"""Kaldi nnet1 TEXT model files for the components on the recipe's path, and the google <-> standard conversion.
+
+Host-only (no GPU): SURVEY.md section 8(f) rank 4.  The reference describes the conversion as manual text editing
+(README.md:19-29 and Q3): `nnet-copy --binary=false`, change `<Transmit>` to `<TimeShift> ... <Shift> k` (k = the
+`--targets-delay` used in training), change `<LstmProjectedStreams>` to `<LstmProjected>` and drop the `<NumStream>` tag.
+Both LSTM components write the same seven parameter blocks in the same order (`w_gifo_x, w_gifo_r, bias, peephole_i_c,
+peephole_f_c, peephole_o_c, w_r_m`: google/nnet/bd-nnet-lstm-projected-streams.h:133-150,
+standard/nnet/nnet-lstm-projected.h:139-152), so the conversion never touches the numbers.
+
+Text layout (upstream nnet-nnet.cc / nnet-component.cc, kaldi-matrix.cc:1172-1211): `<Nnet>`, then per component
+`<Type> output_dim input_dim` followed by the component's own data, then `</Nnet>`.  Matrices are ` [` rows `]`,
+vectors ` [ a b c ]`; reading is whitespace-tokenised and the shapes come from the component header.
+"""
+import numpy as np
+
+LSTM_TYPES = ("<LstmProjectedStreams>", "<LstmProjected>")
+
+
+class NnetComponent:
+    def __init__(self, type_, output_dim, input_dim, attrs=None, arrays=None):
+        self.type = type_                # marker incl. the angle brackets
+        self.output_dim = int(output_dim)
+        self.input_dim = int(input_dim)
+        self.attrs = list(attrs or [])   # ordered (token, value) pairs that follow the dims
+        self.arrays = list(arrays or []) # numpy float32 arrays in file order
+
+    def attr(self, token, default=None):
+        for k, v in self.attrs:
+            if k == token:
+                return v
+        return default
+
+    def __repr__(self):
+        return "NnetComponent(%s %d %d %s, %d arrays)" % (self.type, self.output_dim, self.input_dim, self.attrs,
+                                                        len(self.arrays))
+
+
+def lstm_shapes(output_dim, input_dim, ncell):
+    """Parameter blocks of both LSTM components in file / GetParams order (LPS.h:133-150, :162-189)."""
+    C, R, I = int(ncell), int(output_dim), int(input_dim)
+    return [("w_gifo_x", (4 * C, I)), ("w_gifo_r", (4 * C, R)), ("bias", (4 * C,)), ("peephole_i_c", (C,)),
+            ("peephole_f_c", (C,)), ("peephole_o_c", (C,)), ("w_r_m", (R, C))]
+
+
+class _Tokens:
+    def __init__(self, text):
+        self.t = text.split()
+        self.i = 0
+
+    def peek(self):
+        return self.t[self.i] if self.i < len(self.t) else None
+
+    def next(self):
+        if self.i >= len(self.t):
+            raise RuntimeError("unexpected end of nnet text")
+        self.i += 1
+        return self.t[self.i - 1]
+
+    def expect(self, tok):
+        got = self.next()
+        if got != tok:
+            raise RuntimeError("Expected token %s, got %s" % (tok, got))  # ExpectToken
+
+    def array(self, shape):
+        self.expect("[")
+        n = int(np.prod(shape))
+        vals = self.t[self.i:self.i + n]
+        if len(vals) != n or "]" in vals:
+            raise RuntimeError("matrix/vector in nnet text has the wrong number of elements for shape %s" % (shape,))
+        self.i += n
+        self.expect("]")
+        return np.array(vals, dtype=np.float64).astype(np.float32).reshape(shape)
+
+
+def parse_nnet(text):
+    """Kaldi nnet1 text model -> list of NnetComponent.  Knows the component types of the recipe
+    (google/nnet.proto, standard/nnet.proto): Transmit, TimeShift, LstmProjectedStreams, LstmProjected,
+    AffineTransform, Softmax."""
+    tk = _Tokens(text)
+    tk.expect("<Nnet>")
+    comps = []
+    while True:
+        typ = tk.next()
+        if typ == "</Nnet>":
+            break
+        out_dim, in_dim = int(tk.next()), int(tk.next())
+        c = NnetComponent(typ, out_dim, in_dim)
+        if typ in ("<Transmit>", "<Softmax>"):
+            pass
+        elif typ == "<TimeShift>":
+            tk.expect("<Shift>")                                      # nnet-time-shift.h:33-36
+            c.attrs.append(("<Shift>", int(tk.next())))
+        elif typ in LSTM_TYPES:
+            tk.expect("<CellDim>")                                    # LPS.h:101-104 / nnet-lstm-projected.h:111-113
+            ncell = int(tk.next())
+            c.attrs.append(("<CellDim>", ncell))
+            if typ == "<LstmProjectedStreams>":
+                tk.expect("<NumStream>")
+                c.attrs.append(("<NumStream>", int(tk.next())))
+            for _, shape in lstm_shapes(out_dim, in_dim, ncell):
+                c.arrays.append(tk.array(shape))
+        elif typ == "<AffineTransform>":
+            while tk.peek() in ("<LearnRateCoef>", "<BiasLearnRateCoef>", "<MaxNorm>"):
+                k = tk.next()
+                c.attrs.append((k, float(tk.next())))
+            c.arrays.append(tk.array((out_dim, in_dim)))
+            c.arrays.append(tk.array((out_dim,)))
+        else:
+            raise RuntimeError("Unknown component type %s" % typ)
+        comps.append(c)
+    return comps
+
+
+def _fmt(v):
+    return repr(float(np.float32(v))) if isinstance(v, (float, np.floating)) else str(v)
+
+
+def _array_text(a):
+    a = np.asarray(a, np.float32)
+    if a.ndim == 1:                                                    # VectorBase::Write text: " [ a b c ]\n"
+        return " [ " + " ".join(_fmt(x) for x in a) + " ]\n"
+    rows = ["  " + " ".join(_fmt(x) for x in r) for r in a]            # MatrixBase::Write text, kaldi-matrix.cc:1172-1211
+    return " [\n" + "\n".join(rows) + " ]\n"
+
+
+def format_nnet(comps):
+    out = ["<Nnet> \n"]
+    for c in comps:
+        head = "%s %d %d " % (c.type, c.output_dim, c.input_dim)
+        head += "".join("%s %s " % (k, _fmt(v) if isinstance(v, float) else v) for k, v in c.attrs)
+        if not c.arrays:
+            head += "\n"
+        out.append(head + "".join(_array_text(a) for a in c.arrays))
+    out.append("</Nnet> \n")
+    return "".join(out)
+
+
+def google_to_standard(comps, shift):
+    """README.md:19-29: Transmit -> TimeShift <Shift> shift (= the --targets-delay used in training);
+    LstmProjectedStreams -> LstmProjected without <NumStream>.  Parameters are shared by reference, not copied."""
+    out = []
+    for c in comps:
+        if c.type == "<Transmit>":
+            out.append(NnetComponent("<TimeShift>", c.output_dim, c.input_dim, [("<Shift>", int(shift))]))
+        elif c.type == "<LstmProjectedStreams>":
+            out.append(NnetComponent("<LstmProjected>", c.output_dim, c.input_dim,
+                                     [(k, v) for k, v in c.attrs if k != "<NumStream>"], c.arrays))
+        else:
+            out.append(c)
+    return out
+
+
+def standard_to_google(comps, num_stream):
+    """The inverse edit (README.md Q3): TimeShift -> Transmit (the trainer applies the target delay itself,
+    bd-nnet-train-lstm-streams.cc:198-202), LstmProjected -> LstmProjectedStreams <NumStream> S."""
+    out = []
+    for c in comps:
+        if c.type == "<TimeShift>":
+            out.append(NnetComponent("<Transmit>", c.output_dim, c.input_dim))
+        elif c.type == "<LstmProjected>":
+            attrs = [(k, v) for k, v in c.attrs] + [("<NumStream>", int(num_stream))]
+            out.append(NnetComponent("<LstmProjectedStreams>", c.output_dim, c.input_dim, attrs, c.arrays))
+        else:
+            out.append(c)
+    return out
+
+
+def targets_delay(comps):
+    """The <Shift> of the model's TimeShift component (None when there is none)."""
+    for c in comps:
+        if c.type == "<TimeShift>":
+            return c.attr("<Shift>")
+    return None
+
+
+def lstm_flat_params(comp):
+    """The seven blocks of an LSTM component as one flat float32 vector in GetParams order (LPS.h:162-189): what
+    LstmProjectedStreams.SetParams / lstmp_b200_set_flat take."""
+    assert comp.type in LSTM_TYPES
+    return np.concatenate([np.asarray(a, np.float32).ravel() for a in comp.arrays])
+
+
+def lstm_component_from_flat(flat, output_dim, input_dim, ncell, num_stream=None):
+    flat = np.asarray(flat, np.float32).ravel()
+    need = sum(int(np.prod(shape)) for _, shape in lstm_shapes(output_dim, input_dim, ncell))
+    if need != flat.size:
+        raise RuntimeError("flat parameter vector has %d elements, the component needs %d" % (flat.size, need))
+    arrays, off = [], 0
+    for _, shape in lstm_shapes(output_dim, input_dim, ncell):
+        n = int(np.prod(shape))
+        arrays.append(flat[off:off + n].reshape(shape).copy())
+        off += n
+    attrs = [("<CellDim>", int(ncell))]
+    typ = "<LstmProjected>"
+    if num_stream is not None:
+        attrs.append(("<NumStream>", int(num_stream)))
+        typ = "<LstmProjectedStreams>"
+    return NnetComponent(typ, output_dim, input_dim, attrs, arrays)
+
+
+def time_shift_rows(num_frames, shift):
+    """Row gather of TimeShift::PropagateFnc (standard/nnet/nnet-time-shift.h:42-51): out row dst = in row
+    clamp(dst + shift, 0, num_frames - 1)."""
+    return np.clip(np.arange(num_frames) + int(shift), 0, max(num_frames - 1, 0)).astype(np.int64)

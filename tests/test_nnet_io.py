@@ -1,0 +1,117 @@
+"""Host-only tests of the Kaldi nnet1 text-model reader/writer and the google <-> standard conversion
+(kaldi-lstm_b200/nnet_io.py; reference README.md:19-29, Q3)."""
+import numpy as np
+import pytest
+
+import kaldi_lstm_b200 as klb
+from kaldi_lstm_b200 import nnet_io as nio
+
+
+def _google_model(I=6, C=4, R=3, P=5, S=4, seed=0):
+    rng = np.random.RandomState(seed)
+    n = 4 * C * I + 4 * C * R + 4 * C + 3 * C + R * C
+    flat = rng.randn(n).astype(np.float32) * 0.1
+    lstm = nio.lstm_component_from_flat(flat, R, I, C, num_stream=S)
+    aff = nio.NnetComponent("<AffineTransform>", P, R, [("<LearnRateCoef>", 1.0), ("<BiasLearnRateCoef>", 1.0),
+                                                        ("<MaxNorm>", 0.0)],
+                            [rng.randn(P, R).astype(np.float32), rng.randn(P).astype(np.float32)])
+    return [nio.NnetComponent("<Transmit>", I, I), lstm, aff, nio.NnetComponent("<Softmax>", P, P)], flat
+
+
+def test_text_roundtrip_is_exact():
+    comps, flat = _google_model()
+    text = nio.format_nnet(comps)
+    assert text.startswith("<Nnet>") and text.rstrip().endswith("</Nnet>")
+    assert "<LstmProjectedStreams> 3 6 <CellDim> 4 <NumStream> 4" in text   # README.md:39 header layout
+    back = nio.parse_nnet(text)
+    assert [c.type for c in back] == ["<Transmit>", "<LstmProjectedStreams>", "<AffineTransform>", "<Softmax>"]
+    np.testing.assert_array_equal(nio.lstm_flat_params(back[1]), flat)       # repr(float32) round-trips bit-exactly
+    for a, b in zip(comps[2].arrays, back[2].arrays):
+        np.testing.assert_array_equal(a, b)
+    assert back[2].attr("<MaxNorm>") == 0.0 and back[1].attr("<NumStream>") == 4
+    assert nio.format_nnet(back) == text
+
+
+def test_google_to_standard_and_back():
+    comps, flat = _google_model()
+    std = nio.google_to_standard(comps, shift=5)
+    assert [c.type for c in std] == ["<TimeShift>", "<LstmProjected>", "<AffineTransform>", "<Softmax>"]
+    assert nio.targets_delay(std) == 5 and std[1].attr("<NumStream>") is None and std[1].attr("<CellDim>") == 4
+    text = nio.format_nnet(std)
+    assert "<TimeShift> 6 6 <Shift> 5" in text and "<LstmProjected> 3 6 <CellDim> 4 " in text   # README.md:24-25
+    assert "NumStream" not in text and "Transmit" not in text
+    np.testing.assert_array_equal(nio.lstm_flat_params(nio.parse_nnet(text)[1]), flat)           # numbers untouched
+    goog = nio.standard_to_google(nio.parse_nnet(text), num_stream=4)
+    assert nio.format_nnet(goog) == nio.format_nnet(comps)
+
+
+def test_shapes_and_param_order_match_the_component():
+    names = [n for n, _ in nio.lstm_shapes(512, 40, 800)]
+    assert names == ["w_gifo_x", "w_gifo_r", "bias", "peephole_i_c", "peephole_f_c", "peephole_o_c", "w_r_m"]
+    n = sum(int(np.prod(s)) for _, s in nio.lstm_shapes(512, 40, 800))
+    assert n == 2181600                                                      # 8.726 MB
+    # the oracle's slices (GetParams order, LPS.h:162-189) agree with the file order
+    from oracle import oracle_py
+    sl = oracle_py.param_slices(40, 800, 512)
+    off = 0
+    for name, shape in nio.lstm_shapes(512, 40, 800):
+        a, b = sl[name][0], sl[name][1]
+        assert tuple(sl[name][2]) == tuple(shape)
+        assert a == off and b - a == int(np.prod(shape)), (name, a, b, off)
+        off = b
+
+
+def test_errors():
+    with pytest.raises(RuntimeError):
+        nio.parse_nnet("<Nnet> <Gizmo> 3 3 </Nnet>")
+    with pytest.raises(RuntimeError):   # ExpectToken <NumStream>
+        nio.parse_nnet("<Nnet> <LstmProjectedStreams> 1 1 <CellDim> 1 [ 0 0 0 0 ] </Nnet>")
+    with pytest.raises(RuntimeError):   # wrong element count for the header's shape
+        nio.parse_nnet("<Nnet> <AffineTransform> 2 2 [ 1 2 3 ] [ 0 0 ] </Nnet>")
+    with pytest.raises(RuntimeError):
+        nio.lstm_component_from_flat(np.zeros(7, np.float32), 1, 1, 1)
+
+
+def test_time_shift_rows():
+    # standard/nnet/nnet-time-shift.h:42-51: src = clamp(dst + shift, 0, num_frames - 1)
+    np.testing.assert_array_equal(nio.time_shift_rows(6, 2), [2, 3, 4, 5, 5, 5])
+    np.testing.assert_array_equal(nio.time_shift_rows(4, -1), [0, 0, 1, 2])
+    np.testing.assert_array_equal(nio.time_shift_rows(3, 0), [0, 1, 2])
+    assert klb.nnet_io is nio
+
+
+class _FakeEngine:
+    """Stands in for the CUDA engine so that the component's model-file logic can be exercised on a CPU-only box."""
+
+    def __init__(self, I, C, R, S, T, device=0):
+        self.shape = (I, C, R, S, T)
+        self.num_params = 4 * C * I + 4 * C * R + 4 * C + 3 * C + R * C
+        self.flat = np.zeros(self.num_params, np.float32)
+
+    def set_flat(self, which, a):
+        assert which == 0 and len(a) == self.num_params
+        self.flat = np.asarray(a, np.float32).copy()
+
+    def get_flat(self, which):
+        return self.flat.copy()
+
+
+def test_component_model_file_roundtrip(monkeypatch):
+    from kaldi_lstm_b200 import component
+    monkeypatch.setattr(component, "Engine", _FakeEngine)
+    comps, flat = _google_model()
+    layer = klb.LstmProjectedStreams.FromNnetComponent(comps[1], max_frames=7)
+    assert (layer.input_dim_, layer.ncell_, layer.nrecur_, layer.nstream_) == (6, 4, 3, 4)
+    assert layer.engine.shape == (6, 4, 3, 4, 7)
+    np.testing.assert_array_equal(layer.GetParams(), flat)
+    assert nio.format_nnet([layer.ToNnetComponent()]) == nio.format_nnet([comps[1]])
+    # the standard version's component runs as one stream (S = 1) unless told otherwise
+    std = nio.google_to_standard(comps, 5)
+    one = klb.LstmProjectedStreams.FromNnetComponent(std[1])
+    assert one.nstream_ == 1 and one.engine.shape[3] == 1
+    np.testing.assert_array_equal(one.GetParams(), flat)
+    four = klb.LstmProjectedStreams.FromNnetComponent(std[1], num_stream=4)
+    assert four.ToNnetComponent().attr("<NumStream>") == 4
+    with pytest.raises(RuntimeError):
+        klb.LstmProjectedStreams.FromNnetComponent(comps[0])
+
