@@ -1,0 +1,23 @@
+#!/bin/bash
+# First GPU call of the next round (about 3 minutes of box time): settles the open question of DESIGN.md 3.1b / 6.0.
+#   gpurun --timeout 600 -- 'bash tools/round2_first_call.sh'
+# Needs: make -C kaldi-lstm_b200/csrc all sts ; the two tools/_build binaries (nvcc lines in their headers).
+set -u
+mkdir -p gpurun_out
+timeout 120 tools/_build/tc_pipeline_bench > gpurun_out/tc_pipeline.log 2>&1; cat gpurun_out/tc_pipeline.log
+STS=$PWD/kaldi-lstm_b200/_lib/liblstmp_b200_sts.so
+LSTMP_B200_LIB=$STS timeout -s KILL 300 python -m pytest tests -m gpu -q --tb=short --timeout 150 > gpurun_out/sts_tests.log 2>&1
+tail -3 gpurun_out/sts_tests.log
+for lib in "" "$STS"; do
+  LSTMP_B200_LIB=$lib timeout -s KILL 200 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-e2e --no-secondary \
+    > gpurun_out/bench_lib_$( [ -z "$lib" ] && echo default || echo sts ).json 2>/dev/null
+done
+python - <<'PY'
+import json
+for n in ("default", "sts"):
+    try:
+        d = json.load(open("gpurun_out/bench_lib_%s.json" % n))
+        print(n, round(d["value"]), round(d["ms_per_step"], 3), {k: round(v["us_per_launch"], 1) for k, v in d["kernels"].items()})
+    except Exception as e:
+        print(n, "failed:", e)
+PY
