@@ -408,10 +408,17 @@ extern "C" int lstmp_b200_clone(lstmp_b200_handle_t src, lstmp_b200_handle_t* ou
   int rc = lstmp_b200_create(src->I, src->C, src->R, src->S, src->Tmax, src->device, out);
   if (rc) return rc;
   lstmp_b200_handle_t d = *out;
-  CUDA_TRY(cudaMemcpy(d->params, src->params, src->nparams * sizeof(float), cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(d->corr, src->corr, src->nparams * sizeof(float), cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(d->state_c, src->state_c, (size_t)src->S * src->C * sizeof(float), cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(d->state_r, src->state_r, (size_t)src->S * src->R * sizeof(float), cudaMemcpyDeviceToDevice));
+  cudaError_t e = cudaMemcpy(d->params, src->params, src->nparams * sizeof(float), cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d->corr, src->corr, src->nparams * sizeof(float), cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(d->state_c, src->state_c, (size_t)src->S * src->C * sizeof(float), cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(d->state_r, src->state_r, (size_t)src->S * src->R * sizeof(float), cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) {  // do not leak the half-initialised twin
+    lstmp_b200_destroy(d);
+    *out = nullptr;
+    return fail((int)e, "clone: %s", cudaGetErrorString(e));
+  }
   return 0;
 }
 
@@ -685,7 +692,8 @@ extern "C" int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* inf
   info->max_frames = h->Tmax; info->sm_count = h->sm_count;
   info->ngroups = h->d.ngroups; info->ctas_per_group = h->d.ctas_per_group; info->streams_per_group = h->d.Sg;
   info->cells_per_cta = h->d.cpc; info->rcols_per_cta = h->d.rpc;
-  info->fwd_smem_bytes = h->fwd_smem; info->bwd_smem_bytes = h->bwd_smem;
+  info->fwd_smem_bytes = h->fwd_tc ? h->fwd_tc_smem : h->fwd_smem;
+  info->bwd_smem_bytes = h->bwd_smem;
   info->workspace_bytes = h->workspace_bytes;
   info->kernel_launches = h->launches;
   info->gemm_backend = h->gemm_backend;

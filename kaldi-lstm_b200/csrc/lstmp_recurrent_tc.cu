@@ -504,11 +504,22 @@ bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int staged, 
 }
 
 cudaError_t fwd_tc_set_smem_limit(size_t bytes) {
-  cudaError_t e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  // The attribute is per device and per function and several engines of different shapes may share the process:
+  // only ever raise it (as set_kernel_smem_limits does for the FFMA kernels).
+  static size_t cur[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)bytes);
+  dev &= 63;
+  if (bytes <= cur[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)bytes);
+  if (e != cudaSuccess) return e;
+  cur[dev] = bytes;
+  return cudaSuccess;
 }
 
 cudaError_t launch_fwd_tc(const FwdTcParams& p, size_t smem_bytes, cudaStream_t stream) {
