@@ -91,7 +91,17 @@ struct Timed {
   cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
   Timed(lstmp_b200_engine* h_, int kind_, cudaStream_t st_) : h(h_), kind(kind_), st(st_) {
-    if (h->timing && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+    if (!h->timing) return;
+    if (cudaEventCreate(&a) != cudaSuccess) {
+      a = nullptr;
+      return;
+    }
+    if (cudaEventCreate(&b) != cudaSuccess) {
+      cudaEventDestroy(a);
+      a = b = nullptr;
+      return;
+    }
+    cudaEventRecord(a, st);
   }
   ~Timed() {
     if (a && b) {
@@ -158,6 +168,11 @@ extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
   for (float* b : bufs)
     if (b) cudaFree(b);
   if (h->bar) cudaFree(h->bar);
+  for (auto& e : h->events) {  // timing enabled but never read back
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  h->events.clear();
   if (h->dbg_stamps) {
     cudaDeviceSynchronize();
     std::vector<long long> st(2 + 2 * 1024);
