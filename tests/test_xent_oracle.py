@@ -92,3 +92,52 @@ def test_posterior_to_csr_roundtrip():
     assert rp[0] == 0 and rp[-1] == len(pdf) == len(w) == sum(len(x) for x in post)
     back = [[(int(pdf[e]), float(w[e])) for e in range(rp[t], rp[t + 1])] for t in range(len(post))]
     assert back == [[(int(p), float(np.float32(x))) for p, x in lst] for lst in post]
+
+
+class _FakeXentEngine:
+    """CPU stand-in for the CUDA side (lstmp_b200_xent_*) so that kaldi-lstm_b200/loss.py's host logic -- CSR
+    flattening, assertions, engine (re)creation, Report formatting -- runs on a box without a GPU."""
+
+    def __init__(self, max_frames, device=0):
+        if max_frames <= 0:
+            raise ValueError("max_frames")
+        self.max_frames = max_frames
+        self.o = xent_oracle.XentOracle()
+        self.calls = 0
+
+    def eval_masked(self, mask, net_out, row_ptr, pdf, weight, diff):
+        assert net_out.shape[0] <= self.max_frames
+        post = [[(int(pdf[e]), float(weight[e])) for e in range(row_ptr[t], row_ptr[t + 1])]
+                for t in range(len(row_ptr) - 1)]
+        diff.copy_(torch.from_numpy(self.o.eval_masked(mask, net_out.numpy(), post)))
+        self.calls += 1
+
+    def stats(self):
+        return {"loss": self.o.loss, "entropy": self.o.entropy, "correct": self.o.correct, "frames": self.o.frames,
+                "kernel_launches": 2 * self.calls}
+
+
+def test_python_mirror_host_logic(monkeypatch):
+    import kaldi_lstm_b200 as klb
+    from kaldi_lstm_b200 import loss
+    monkeypatch.setattr(loss, "XentEngine", _FakeXentEngine)
+    mask, y, post = xent_oracle.random_case(12, 9, seed=8, soft=True, empty_every=5, dup_every=4)
+    ref = xent_oracle.XentOracle()
+    want = ref.eval_masked(mask, y, post)
+    x = klb.Xent()                                   # engine created on first use, sized by the call
+    d1 = x.EvalMasked(mask, torch.from_numpy(y), post)
+    np.testing.assert_array_equal(d1.numpy(), want)
+    d2 = torch.empty(12, 9)
+    out = x.EvalMasked(mask, torch.from_numpy(y), klb.posterior_to_csr(post), d2)   # pre-flattened posterior, caller's diff
+    assert out is d2
+    np.testing.assert_array_equal(d2.numpy(), want)
+    s = x.Stats()
+    assert s["frames"] == 2 * ref.frames and s["correct"] == 2 * ref.correct and abs(s["loss"] - 2 * ref.loss) < 1e-9
+    rep = x.Report()
+    assert rep.startswith("AvgLoss: ") and "(Xent), [AvgXent: " in rep and "FRAME_ACCURACY >> " in rep   # :293-307
+    with pytest.raises(AssertionError):              # KALDI_ASSERT(num_frames == post.size())   nnet-loss.cc:80
+        x.EvalMasked(mask, torch.from_numpy(y), post[:-1])
+    with pytest.raises(RuntimeError):                # pdf-id outside the network output            :88-91
+        x.EvalMasked(mask, torch.from_numpy(y), [[(9, 1.0)]] + post[1:])
+    assert klb.Xent().Stats()["frames"] == 0 and "nan" in klb.Xent().Report()
+
