@@ -7,7 +7,7 @@
       -o gpurun_out/prof_rN python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
 
 usage: tools/make_profiles.py <round> [launches.csv] [prof.ncu-rep]
-writes profiles/rN_launches.csv, rN_launch_summary.md, rN_ncu_set_full_selected.csv, traffic.json
+writes profiles/rN_launches.csv, rN_launch_summary.md, rN_ncu_set_full_selected.csv, rN_ncu_digest.md, traffic.json
 """
 import collections
 import csv
@@ -110,9 +110,63 @@ def full_selected(rnd, rep):
     return traffic
 
 
+def ncu_summary(rnd, rep):
+    """Human-readable digest of the --set full capture: one block per kernel (first captured launch of each)."""
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True,
+                         check=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, m):
+        try:
+            return float(r[col[m]].replace(",", ""))
+        except Exception:
+            return None
+
+    stalls = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+    out = ["# Round %s ncu --set full digest (tools/make_profiles.py; source: gpurun_out/prof_r%s.ncu-rep, command in"
+           % (rnd, rnd), "# tools/make_profiles.py's header; per-launch values of the FIRST captured launch of each kernel)", ""]
+    seen = set()
+    for r in data:
+        name = r[col["Kernel Name"]].split("(")[0]
+        if name in seen:
+            continue
+        seen.add(name)
+        g = lambda m: val(r, m)
+        out.append("## `%s`" % name)
+        out.append("")
+        out.append("| metric | value |")
+        out.append("|---|---|")
+        dur = g("gpu__time_duration.sum")
+        unit = units[col["gpu__time_duration.sum"]]
+        out.append("| duration | %.1f %s |" % (dur, unit))
+        out.append("| grid x block, regs/thread, dynamic smem | %d x %d, %d, %.1f KB |" % (
+            g("launch__grid_size"), g("launch__block_size"), g("launch__registers_per_thread"),
+            g("launch__shared_mem_per_block_dynamic")))
+        rd, wr = g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
+        out.append("| DRAM read / write | %.2f %s / %.2f %s (%.1f %% of peak throughput) |" % (
+            rd, units[col["dram__bytes_read.sum"]], wr, units[col["dram__bytes_write.sum"]],
+            g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")))
+        out.append("| L2 hit rate | %.1f %% |" % g("lts__t_sector_hit_rate.pct"))
+        out.append("| issue slots busy | %.1f %% |" % g("smsp__issue_active.avg.pct_of_peak_sustained_active"))
+        out.append("| tensor pipe / FMA pipe active | %.1f %% / %.1f %% |" % (
+            g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") or 0.0,
+            g("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active") or 0.0))
+        wf, bc = g("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), g("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")
+        if wf:
+            out.append("| shared-memory wavefronts (LSU) / of which bank conflicts | %.3g / %.3g (%.0f %%) |" % (wf, bc, 100.0 * bc / wf))
+        top = sorted(((g(m) or 0.0, m) for m in stalls), reverse=True)[:5]
+        out.append("| top stall reasons (warps per issue) | %s |" % ", ".join(
+            "%s %.2f" % (m[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], v) for v, m in top))
+        out.append("")
+    open(os.path.join(ROOT, "profiles", "r%s_ncu_digest.md" % rnd), "w").write("\n".join(out) + "\n")
+
+
 if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "1"
     lcsv = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches_r%s.csv" % rnd)
     rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "prof_r%s.ncu-rep" % rnd)
     print(launch_summary(rnd, lcsv))
     print(full_selected(rnd, rep))
+    ncu_summary(rnd, rep)
