@@ -9,6 +9,8 @@
 //   staged   : cp.async landing slots + read-back (1) vs LDG.128 register prefetch (0)
 //   mma      : issue the MMAs (1) or commit immediately (0: pure loader + handshake cost)
 //   nslot    : ring depth
+//   relay    : proxy fence in a relay warp (1, what the kernel does) or in the issuer warp after its acquire-wait (0)
+//   N        : MMA N (48 = gate product, 16 = projection)
 //
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -I kaldi-lstm_b200/csrc -o tools/_build/tc_pipeline_bench tools/tc_pipeline_bench.cu
 #include <cstdio>
@@ -28,7 +30,7 @@ __device__ __forceinline__ void split4(float4 x, float4& h, float4& l) {
 
 template <bool GENERIC>
 __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int K, int reps, int staged, int mma,
-                                               int nslot, long long* out) {
+                                               int nslot, int relay, int N, long long* out) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* base;
   if (GENERIC) base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,9 +111,14 @@ __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int 
       }
     } else if (warp == 8) {
       const uint32_t ring_s = smem_u32(ring), w_s = smem_u32(wts);
-      const uint32_t idesc = idesc_tf32(128, 48);
+      const uint32_t idesc = idesc_tf32(128, N);
       for (int c = 0; c < nch; ++c) {
-        mbar_wait(&ready[slot], use & 1);
+        if (relay) {
+          mbar_wait(&ready[slot], use & 1);
+        } else {
+          mbar_wait(&full[slot], use & 1);
+          fence_async_smem();
+        }
         tc_fence_after();
         if (mma) {
           const uint32_t a0 = ring_s + slot * SLOT, b0 = w_s + (uint32_t)(c & 15) * 6144u;
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int 
         if (++slot == (uint32_t)nslot) { slot = 0; ++use; }
       }
       tc_fence_before();
-    } else if (warp == 9) {
+    } else if (warp == 9 && relay) {
       for (int c = 0; c < nch; ++c) {
         mbar_wait(&full[slot], use & 1);
         fence_async_smem();
@@ -164,21 +171,29 @@ int main() {
   const size_t smem = 96 * 1024 + MAXSLOT * SLOT + PF * STAGE + 1024 + 1024;
   cudaFuncSetAttribute((const void*)pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute((const void*)pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  struct Cfg { int generic, staged, mma, nslot, relay, N; };
+  std::vector<Cfg> cfgs;
   for (int generic = 1; generic >= 0; --generic)
-    for (int staged = 1; staged >= 0; --staged)
-      for (int mma = 1; mma >= 0; --mma)
-        for (int nslot : {3, 6}) {
-          for (int it = 0; it < 2; ++it) {
-            if (generic) pipe<true><<<nsm, 384, smem>>>(X, K, reps, staged, mma, nslot, out);
-            else pipe<false><<<nsm, 384, smem>>>(X, K, reps, staged, mma, nslot, out);
-          }
-          cudaError_t e = cudaDeviceSynchronize();
-          std::vector<long long> h(nsm);
-          cudaMemcpy(h.data(), out, nsm * sizeof(long long), cudaMemcpyDeviceToHost);
-          long long mx = 0;
-          for (auto c : h) mx = c > mx ? c : mx;
-          printf("%s smem ptrs, %s, mma %d, %d slots: %7.1f cycles per 8 KB chunk (%s)\n", generic ? "generic" : "shared ",
-                 staged ? "cp.async staged" : "LDG registers  ", mma, nslot, (double)mx / (reps * (K / KC)), cudaGetErrorString(e));
-        }
+    for (int staged = 1; staged >= 0; --staged) {
+      cfgs.push_back({generic, staged, 1, 3, 1, 48});   // the shipped configuration (generic, staged) and its variants
+      cfgs.push_back({generic, staged, 1, 6, 1, 48});
+      cfgs.push_back({generic, staged, 0, 3, 1, 48});   // no MMAs: loader + handshake cost alone
+      cfgs.push_back({generic, staged, 1, 3, 0, 48});   // fence in the issuer instead of the relay warp
+      cfgs.push_back({generic, staged, 1, 3, 1, 16});   // projection-sized MMAs
+    }
+  for (const Cfg& c : cfgs) {
+    for (int it = 0; it < 2; ++it) {
+      if (c.generic) pipe<true><<<nsm, 384, smem>>>(X, K, reps, c.staged, c.mma, c.nslot, c.relay, c.N, out);
+      else pipe<false><<<nsm, 384, smem>>>(X, K, reps, c.staged, c.mma, c.nslot, c.relay, c.N, out);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(nsm);
+    cudaMemcpy(h.data(), out, nsm * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (auto v : h) mx = v > mx ? v : mx;
+    printf("%s smem ptrs, %s, mma %d (N=%2d), %d slots, %s: %7.1f cycles per 8 KB chunk (%s)\n",
+           c.generic ? "generic" : "shared ", c.staged ? "cp.async staged" : "LDG registers  ", c.mma, c.N, c.nslot,
+           c.relay ? "relay fence " : "issuer fence", (double)mx / (reps * (K / KC)), cudaGetErrorString(e));
+  }
   return 0;
 }
