@@ -517,6 +517,30 @@ def main():
                                   "ms_per_step": m2 / n2, "steps": n2}}
         except Exception as e:  # never let the secondary measurement break the contract line
             secondary = {"cfg2": {"error": str(e)[:200]}}
+        # forward-only (cross-validate mode) frames/s of the main workload, device-resident inputs
+        try:
+            def fwd_only(i):
+                flags = [1 if (i + s) % 50 == 0 else 0 for s in range(S)]
+                hcur = X[i % ring]
+                for li, comp in enumerate(layers):
+                    comp.Reset(flags)
+                    comp.PropagateFnc(hcur, outs[li])
+                    hcur = outs[li]
+            for i in range(5):
+                fwd_only(i)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nf = 100
+            f0.record()
+            for i in range(nf):
+                fwd_only(i)
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1)
+            secondary["forward_only"] = {"workload": wl["desc"] + " -- Reset + Propagate only", "value": rows * nf / (fms * 1e-3),
+                                         "unit": "frames/s", "ms_per_step": fms / nf, "steps": nf}
+        except Exception as e:
+            secondary["forward_only"] = {"error": str(e)[:200]}
 
     if rank == 0:
         info = layers[0].engine.info()
