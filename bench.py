@@ -168,6 +168,20 @@ def run_reference_arm(args, wl):
         stack.step()
     dt = time.perf_counter() - t0
     val = stack.frames() * args.steps / dt
+    # Kaldi's nnet1 default is a single-threaded BLAS: time a short single-thread sample as well
+    single = None
+    try:
+        from oracle import oracle_py
+        if oracle_py.use_openblas(1):
+            t1 = time.perf_counter()
+            n1 = 0
+            while n1 < 1 or (time.perf_counter() - t1 < 2.0 and n1 < 20):
+                stack.step()
+                n1 += 1
+            single = {"value": stack.frames() * n1 / (time.perf_counter() - t1), "unit": "frames/s", "cores": 1,
+                      "sample": "%d full chunks" % n1}
+    except Exception as e:
+        single = {"error": str(e)[:200]}
     line = {
         "impl": "reference", "metric": "frames/sec LstmProjectedStreams 800-cell/512-proj BPTT", "value": val,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -176,7 +190,7 @@ def run_reference_arm(args, wl):
         "config": {"workload": wl["desc"], "name": args.workload, "num_stream": wl["S"], "bptt_frames": wl["T"]},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": stack.threads, "kind": "port",
                          "sample": "%d full chunks of the workload; sgemm=%s, elementwise loops serial as in "
-                                   "kaldi-matrix.cc" % (args.steps, stack.blas)},
+                                   "kaldi-matrix.cc" % (args.steps, stack.blas), "single_thread": single},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference cannot be compiled here (no Kaldi tree); this is the oracle restatement of its CPU "
                 "matrix path (oracle/lstmp_streams_oracle.c) on %d host threads (host has %d)" % (stack.threads,
