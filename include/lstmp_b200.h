@@ -170,16 +170,16 @@ int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, int N, int K
  * stride ld_out), diff [num_frames x num_pdf] (device, fully written) = frame_mask * (net_out - target).  The Kaldi
  * `Posterior` (host std::vector<std::vector<std::pair<int32,BaseFloat>>>) is passed flattened as CSR:
  * post_row_ptr[num_frames + 1], post_pdf[nnz], post_weight[nnz] (host; duplicates of a pdf within a frame accumulate,
- * nnet-loss.cc:94); frame_mask is the host Vector of 0/1 floats (nnet-loss.cc:76, :98-100).  A pdf-id outside
+ * nnet-loss.cc:93); frame_mask is the host Vector of 0/1 floats (nnet-loss.cc:76, :98-100).  A pdf-id outside
  * [0, num_pdf) is the reference's KALDI_ERR (:88-91) -> LSTMP_B200_EINVAL.  Statistics accumulate on the device
  * (loss_, entropy_ in double; correct_, frames_) and are read back only by lstmp_b200_xent_get_stats.
  * The call is asynchronous on `stream`; the host arrays may be reused as soon as it returns. */
 typedef struct lstmp_b200_xent* lstmp_b200_xent_handle_t;
 typedef struct {
-  double loss;      /* loss_    : -sum mask * t * log(y)                 (nnet-loss.cc:127-131,141) */
-  double entropy;   /* entropy_ : -sum mask * t * log(t + 1e-20)         (:134-139,142) */
-  long long correct;/* correct_ : valid frames whose arg-max matches the target's      (:109-124,143) */
-  long long frames; /* frames_  : sum over calls of (int32) sum(frame_mask)            (:144-145) */
+  double loss;      /* loss_    : -sum mask * t * log(y)                 (nnet-loss.cc:123-128,138) */
+  double entropy;   /* entropy_ : -sum mask * t * log(t + 1e-20)         (:130-136,139) */
+  long long correct;/* correct_ : valid frames whose arg-max matches the target's      (:108-121,140) */
+  long long frames; /* frames_  : sum over calls of (int32) sum(frame_mask)            (:141-142) */
   unsigned long long kernel_launches;
 } lstmp_b200_xent_stats_t;
 int lstmp_b200_xent_create(int max_frames, int device, lstmp_b200_xent_handle_t* out);

@@ -11,7 +11,7 @@
 //
 // Numerics follow the reference's CPU matrix path: t*log(y) and t*log(t + 1e-20) in fp32 per entry, summed in
 // double; argmax = first column holding the row maximum (cu-matrix.cc:1333-1343); duplicate pdf-ids in one frame
-// accumulate (nnet-loss.cc:94).  Where the reference's DENSE formulation yields NaN (softmax underflow y == 0 at a
+// accumulate (nnet-loss.cc:93).  Where the reference's DENSE formulation yields NaN (softmax underflow y == 0 at a
 // column with t == 0: 0 * log(0)), the sparse formulation contributes 0.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kThreads) xent_rows_kernel(const float* __rest
       for (int q = e; q < end; ++q)
         if (pdf[q] == p) t += weight[q];
       dr[p] = (yr[p] - t) * m;                          // diff = (y - t) * mask, same rounding     :103-106
-      xe += (logf(yr[p]) * t) * m;                      // t * log(y), masked                     :127-131
-      en += (logf(t + 1e-20f) * t) * m;                 // t * log(t + 1e-20), masked             :134-139
+      xe += (logf(yr[p]) * t) * m;                      // t * log(y), masked                     :123-128
+      en += (logf(t + 1e-20f) * t) * m;                 // t * log(t + 1e-20), masked             :130-136
       if (t > tmax || (t == tmax && p < tmax_id)) {
         tmax = t;
         tmax_id = p;
@@ -124,12 +124,12 @@ __global__ void __launch_bounds__(kThreads) xent_rows_kernel(const float* __rest
     }
     row_xent[r] = xe;
     row_ent[r] = en;
-    row_correct[r] = (m == 1.0f && tgt_id == best_id) ? 1 : 0;                              // :120-124
+    row_correct[r] = (m == 1.0f && tgt_id == best_id) ? 1 : 0;                              // :117-121
   }
 }
 
 // Fixed-order reduction of the per-row statistics into the accumulators (deterministic, no atomics).
-// acc[0] += -sum xent, acc[1] += -sum ent ; cnt[0] += correct, cnt[1] += (int) sum(mask)     :141-146
+// acc[0] += -sum xent, acc[1] += -sum ent ; cnt[0] += correct, cnt[1] += (int) sum(mask)     :138-142
 __global__ void __launch_bounds__(kThreads) xent_reduce_kernel(int rows, const float* __restrict__ row_xent,
                                                                const float* __restrict__ row_ent,
                                                                const int* __restrict__ row_correct,

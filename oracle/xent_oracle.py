@@ -20,7 +20,7 @@ class XentOracle:
 
     @staticmethod
     def _find_row_max_id(m):
-        # CuMatrixBase::FindRowMaxId, CPU branch (google/cudamatrix/cu-matrix.cc:1327-1346): strict '<' scan from
+        # CuMatrixBase::FindRowMaxId, CPU branch (google/cudamatrix/cu-matrix.cc:1327-1345): strict '<' scan from
         # column 0 starting at -1e21, i.e. the FIRST column holding the row maximum (np.argmax has the same rule)
         return np.argmax(m, axis=1).astype(np.int32)
 
@@ -41,16 +41,16 @@ class XentOracle:
                 tgt[t, pdf] += np.float32(w)
         # derivative wrt. the activations of the last layer, masked           :103-106
         diff = (net_out - tgt) * mask[:, None]
-        # frames where the maxima match, valid frames only                    :109-124
+        # frames where the maxima match, valid frames only                    :108-121
         mo, mt = self._find_row_max_id(net_out), self._find_row_max_id(tgt)
         correct = int(np.sum((mask == 1.0) & (mo == mt)))
-        # cross entropy and entropy                                            :127-139
+        # cross entropy and entropy                                            :123-136
         with np.errstate(divide="ignore", invalid="ignore"):
             xe = (np.log(net_out) * tgt) * mask[:, None]
             en = (np.log(tgt + np.float32(1e-20)) * tgt) * mask[:, None]
         cross_entropy = -float(np.sum(xe, dtype=np.float64))
         entropy = -float(np.sum(en, dtype=np.float64))
-        self.loss += cross_entropy                                           # :141-146
+        self.loss += cross_entropy                                           # :138-142
         self.entropy += entropy
         self.correct += correct
         self.frames += int(np.float32(mask.sum(dtype=np.float64)))
@@ -83,7 +83,7 @@ def random_case(rows, num_pdf, seed=0, soft=False, empty_every=0, dup_every=0, m
         else:
             lst = [(int(rng.randint(0, num_pdf)), 1.0)]
         if dup_every and t % dup_every == 0:
-            lst.append((lst[0][0], 0.25))  # duplicate pdf in one frame: weights accumulate (:94)
+            lst.append((lst[0][0], 0.25))  # duplicate pdf in one frame: weights accumulate (:93)
         post.append(lst)
     mask = np.ones(rows, np.float32)
     if mask_every:
