@@ -9,7 +9,9 @@
 //   staged   : cp.async landing slots + read-back (1) vs LDG.128 register prefetch (0)
 //   mma      : issue the MMAs (1) or commit immediately (0: pure loader + handshake cost)
 //   nslot    : ring depth
-//   relay    : proxy fence in a relay warp (1, what the kernel does) or in the issuer warp after its acquire-wait (0)
+//   relay    : proxy fence in a relay warp (1, what the kernel does), in the issuer warp after its acquire-wait (0),
+//              in THREE relay warps taking the chunks round-robin (3), or no fence at all (-1: timing only, the MMAs may
+//              then read stale data) -- is one fence.proxy.async per chunk on a single warp the 600-cycle limiter?
 //   N        : MMA N (48 = gate product, 16 = projection)
 //
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -I kaldi-lstm_b200/csrc -o tools/_build/tc_pipeline_bench tools/tc_pipeline_bench.cu
@@ -113,11 +115,11 @@ __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int 
       const uint32_t ring_s = smem_u32(ring), w_s = smem_u32(wts);
       const uint32_t idesc = idesc_tf32(128, N);
       for (int c = 0; c < nch; ++c) {
-        if (relay) {
+        if (relay > 0) {
           mbar_wait(&ready[slot], use & 1);
         } else {
           mbar_wait(&full[slot], use & 1);
-          fence_async_smem();
+          if (relay == 0) fence_async_smem();
         }
         tc_fence_after();
         if (mma) {
@@ -132,11 +134,13 @@ __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int 
         if (++slot == (uint32_t)nslot) { slot = 0; ++use; }
       }
       tc_fence_before();
-    } else if (warp == 9 && relay) {
+    } else if (relay > 0 && warp >= 9 && warp < 9 + relay) {
       for (int c = 0; c < nch; ++c) {
-        mbar_wait(&full[slot], use & 1);
-        fence_async_smem();
-        if (lane == 0) mbar_arrive(&ready[slot]);
+        if (c % relay == warp - 9) {  // relay == 3: warps 9, 10, 11 take the chunks round-robin
+          mbar_wait(&full[slot], use & 1);
+          fence_async_smem();
+          if (lane == 0) mbar_arrive(&ready[slot]);
+        }
         if (++slot == (uint32_t)nslot) { slot = 0; ++use; }
       }
     }
@@ -159,6 +163,18 @@ __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int 
   }
 }
 
+// cycles per fence.proxy.async executed back to back by one warp, alone (mode 0) or after one STS.128 per lane (mode 1)
+__global__ void fence_cost(int mode, int n, long long* out) {
+  __shared__ float4 buf[32];
+  long long t0 = clock64();
+  for (int i = 0; i < n; ++i) {
+    if (mode) buf[threadIdx.x & 31] = make_float4((float)i, 0.f, 0.f, 0.f);
+    fence_async_smem();
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
 int main() {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, 0);
@@ -171,6 +187,14 @@ int main() {
   const size_t smem = 96 * 1024 + MAXSLOT * SLOT + PF * STAGE + 1024 + 1024;
   cudaFuncSetAttribute((const void*)pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute((const void*)pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int mode = 0; mode < 2; ++mode) {
+    fence_cost<<<1, 32>>>(mode, 1000, out);
+    fence_cost<<<1, 32>>>(mode, 1000, out);
+    cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, out, sizeof c, cudaMemcpyDeviceToHost);
+    printf("fence.proxy.async (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC)%s: %.1f cycles each\n", mode ? " after an STS.128" : "", c / 1000.0);
+  }
   struct Cfg { int generic, staged, mma, nslot, relay, N; };
   std::vector<Cfg> cfgs;
   for (int generic = 1; generic >= 0; --generic)
@@ -179,6 +203,8 @@ int main() {
       cfgs.push_back({generic, staged, 1, 6, 1, 48});
       cfgs.push_back({generic, staged, 0, 3, 1, 48});   // no MMAs: loader + handshake cost alone
       cfgs.push_back({generic, staged, 1, 3, 0, 48});   // fence in the issuer instead of the relay warp
+      cfgs.push_back({generic, staged, 1, 3, 3, 48});   // three relay warps
+      cfgs.push_back({generic, staged, 1, 3, -1, 48});  // no proxy fence at all (timing only)
       cfgs.push_back({generic, staged, 1, 3, 1, 16});   // projection-sized MMAs
     }
   for (const Cfg& c : cfgs) {
@@ -193,7 +219,7 @@ int main() {
     for (auto v : h) mx = v > mx ? v : mx;
     printf("%s smem ptrs, %s, mma %d (N=%2d), %d slots, %s: %7.1f cycles per 8 KB chunk (%s)\n",
            c.generic ? "generic" : "shared ", c.staged ? "cp.async staged" : "LDG registers  ", c.mma, c.N, c.nslot,
-           c.relay ? "relay fence " : "issuer fence", (double)mx / (reps * (K / KC)), cudaGetErrorString(e));
+           c.relay == 1 ? "relay fence " : c.relay == 3 ? "3 relay warps" : c.relay == 0 ? "issuer fence" : "NO fence    ", (double)mx / (reps * (K / KC)), cudaGetErrorString(e));
   }
   return 0;
 }
