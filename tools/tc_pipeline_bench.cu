@@ -168,7 +168,7 @@ __global__ void fence_cost(int mode, int n, long long* out) {
   __shared__ float4 buf[32];
   long long t0 = clock64();
   for (int i = 0; i < n; ++i) {
-    if (mode) buf[threadIdx.x & 31] = make_float4((float)i, 0.f, 0.f, 0.f);
+    if (mode) asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n" ::"r"(smem_u32(&buf[threadIdx.x & 31])), "f"((float)i) : "memory");
     fence_async_smem();
   }
   long long t1 = clock64();
