@@ -13,6 +13,10 @@
 //              in THREE relay warps taking the chunks round-robin (3), or no fence at all (-1: timing only, the MMAs may
 //              then read stale data) -- is one fence.proxy.async per chunk on a single warp the 600-cycle limiter?
 //   N        : MMA N (48 = gate product, 16 = projection)
+//   wpc      : WARP-PER-CHUNK loaders (1): warp w loads, splits and stores chunks c = w (mod 8) on its own (16 units per
+//              lane, full-barrier count 1), so eight chunks are in progress at once -- in the shipped layout (0) every
+//              loader warp takes part in every chunk and a chunk cannot finish faster than one warp's dependent chain
+//              wait -> read back -> split -> store -> arrive
 //
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -I kaldi-lstm_b200/csrc -o tools/_build/tc_pipeline_bench tools/tc_pipeline_bench.cu
 #include <cstdio>
@@ -21,7 +25,7 @@
 using namespace lstmp;
 using namespace lstmp::tc;
 
-constexpr int KC = 32, S = 64, LOADERS = 256, PF = 3, MAXSLOT = 6;
+constexpr int KC = 32, S = 64, LOADERS = 256, PF = 3, MAXSLOT = 8;
 constexpr uint32_t SLOT = 128 * 128, STAGE = S * 8 * 16;
 
 __device__ __forceinline__ void split4(float4 x, float4& h, float4& l) {
@@ -32,13 +36,13 @@ __device__ __forceinline__ void split4(float4 x, float4& h, float4& l) {
 
 template <bool GENERIC>
 __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int K, int reps, int staged, int mma,
-                                               int nslot, int relay, int N, long long* out) {
+                                               int nslot, int relay, int N, int wpc, long long* out) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* base;
   if (GENERIC) base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   else base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* wts = base;                       // 48 rows x 128 B per chunk x 16 chunks (stationary B operand)
-  uint8_t* ring = base + 96 * 1024;
+  uint8_t* wts = base;                       // one 48-row x 128 B tile, reused for every chunk (timing only)
+  uint8_t* ring = base + 8 * 1024;
   uint8_t* stage = ring + MAXSLOT * SLOT;    // PF landing slots
   uint64_t* full = reinterpret_cast<uint64_t*>(stage + PF * STAGE);
   uint64_t* ready = full + MAXSLOT;
@@ -47,14 +51,14 @@ __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid == 0) {
-    for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], LOADERS / 32); mbar_init(&ready[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], wpc ? 1 : LOADERS / 32); mbar_init(&ready[s], 1); mbar_init(&empty[s], 1); }
     fence_mbar_init();
   }
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(64) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  for (int i = tid; i < 96 * 1024 / 4; i += 384) reinterpret_cast<float*>(wts)[i] = 0.001f;
+  for (int i = tid; i < 8 * 1024 / 4; i += 384) reinterpret_cast<float*>(wts)[i] = 0.001f;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -65,7 +69,31 @@ __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int 
   long long t0 = clock64();
   for (int rep = 0; rep < reps; ++rep) {
     uint32_t slot = cc % (uint32_t)nslot, use = cc / (uint32_t)nslot;
-    if (warp < 8) {
+    if (warp < 8 && wpc) {
+      // warp-per-chunk: this warp owns chunks c = warp (mod 8); lane l owns units u = l + 32 i (row u >> 3, 16-byte
+      // column u & 7), loads them with LDG.128, splits and stores hi / lo, then lane 0 arrives (count 1)
+      const int kc = lane & 7;
+      for (int c = 0; c < nch; ++c) {
+        if ((c & 7) == warp) {
+          float4 x[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = ld_cg_f4(X + (size_t)((lane >> 3) + 4 * i) * K + c * KC + 4 * kc);
+          if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+          uint8_t* st = ring + (size_t)slot * SLOT;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = (lane >> 3) + 4 * i;
+            float4 h, l;
+            split4(x[i], h, l);
+            *reinterpret_cast<float4*>(st + sw128_off(r, kc)) = h;
+            *reinterpret_cast<float4*>(st + sw128_off(r, kc) + S * 128) = l;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[slot]);
+        }
+        if (++slot == (uint32_t)nslot) { slot = 0; ++use; }
+      }
+    } else if (warp < 8) {
       const int r0 = tid >> 3, r1 = r0 + 32, kc = tid & 7;
       const float* g0 = X + (size_t)r0 * K + 4 * kc;
       const float* g1 = X + (size_t)r1 * K + 4 * kc;
@@ -123,7 +151,7 @@ __global__ void __launch_bounds__(384, 1) pipe(const float* __restrict__ X, int 
         }
         tc_fence_after();
         if (mma) {
-          const uint32_t a0 = ring_s + slot * SLOT, b0 = w_s + (uint32_t)(c & 15) * 6144u;
+          const uint32_t a0 = ring_s + slot * SLOT, b0 = w_s;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (elect_one()) mma_tf32(tmem, make_desc_sw128(a0 + 32 * j), make_desc_sw128(b0 + 32 * j), idesc, (c | j) ? 1u : 0u);
@@ -184,7 +212,7 @@ int main() {
   cudaMalloc(&X, (size_t)S * 800 * 4);
   cudaMemset(X, 0, (size_t)S * 800 * 4);
   cudaMalloc(&out, nsm * sizeof(long long));
-  const size_t smem = 96 * 1024 + MAXSLOT * SLOT + PF * STAGE + 1024 + 1024;
+  const size_t smem = 8 * 1024 + MAXSLOT * SLOT + PF * STAGE + 1024 + 1024;
   cudaFuncSetAttribute((const void*)pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute((const void*)pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int mode = 0; mode < 2; ++mode) {
@@ -195,22 +223,27 @@ int main() {
     cudaMemcpy(&c, out, sizeof c, cudaMemcpyDeviceToHost);
     printf("fence.proxy.async (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC)%s: %.1f cycles each\n", mode ? " after an STS.128" : "", c / 1000.0);
   }
-  struct Cfg { int generic, staged, mma, nslot, relay, N; };
+  struct Cfg { int generic, staged, mma, nslot, relay, N, wpc; };
   std::vector<Cfg> cfgs;
   for (int generic = 1; generic >= 0; --generic)
     for (int staged = 1; staged >= 0; --staged) {
-      cfgs.push_back({generic, staged, 1, 3, 1, 48});   // the shipped configuration (generic, staged) and its variants
-      cfgs.push_back({generic, staged, 1, 6, 1, 48});
-      cfgs.push_back({generic, staged, 0, 3, 1, 48});   // no MMAs: loader + handshake cost alone
-      cfgs.push_back({generic, staged, 1, 3, 0, 48});   // fence in the issuer instead of the relay warp
-      cfgs.push_back({generic, staged, 1, 3, 3, 48});   // three relay warps
-      cfgs.push_back({generic, staged, 1, 3, -1, 48});  // no proxy fence at all (timing only)
-      cfgs.push_back({generic, staged, 1, 3, 1, 16});   // projection-sized MMAs
+      cfgs.push_back({generic, staged, 1, 3, 1, 48, 0});   // the shipped configuration (generic, staged) and its variants
+      cfgs.push_back({generic, staged, 1, 6, 1, 48, 0});
+      cfgs.push_back({generic, staged, 0, 3, 1, 48, 0});   // no MMAs: loader + handshake cost alone
+      cfgs.push_back({generic, staged, 1, 3, 0, 48, 0});   // fence in the issuer instead of the relay warp
+      cfgs.push_back({generic, staged, 1, 3, 3, 48, 0});   // three relay warps
+      cfgs.push_back({generic, staged, 1, 3, -1, 48, 0});  // no proxy fence at all (timing only)
+      cfgs.push_back({generic, staged, 1, 3, 1, 16, 0});   // projection-sized MMAs
+      if (!staged) {
+        cfgs.push_back({generic, 0, 1, 8, 1, 48, 1});      // warp-per-chunk loaders, 8 slots
+        cfgs.push_back({generic, 0, 1, 8, 3, 48, 1});      // ... with three relay warps
+        cfgs.push_back({generic, 0, 0, 8, 1, 48, 1});      // ... without MMAs
+      }
     }
   for (const Cfg& c : cfgs) {
     for (int it = 0; it < 2; ++it) {
-      if (c.generic) pipe<true><<<nsm, 384, smem>>>(X, K, reps, c.staged, c.mma, c.nslot, c.relay, c.N, out);
-      else pipe<false><<<nsm, 384, smem>>>(X, K, reps, c.staged, c.mma, c.nslot, c.relay, c.N, out);
+      if (c.generic) pipe<true><<<nsm, 384, smem>>>(X, K, reps, c.staged, c.mma, c.nslot, c.relay, c.N, c.wpc, out);
+      else pipe<false><<<nsm, 384, smem>>>(X, K, reps, c.staged, c.mma, c.nslot, c.relay, c.N, c.wpc, out);
     }
     cudaError_t e = cudaDeviceSynchronize();
     std::vector<long long> h(nsm);
@@ -218,7 +251,7 @@ int main() {
     long long mx = 0;
     for (auto v : h) mx = v > mx ? v : mx;
     printf("%s smem ptrs, %s, mma %d (N=%2d), %d slots, %s: %7.1f cycles per 8 KB chunk (%s)\n",
-           c.generic ? "generic" : "shared ", c.staged ? "cp.async staged" : "LDG registers  ", c.mma, c.N, c.nslot,
+           c.generic ? "generic" : "shared ", c.wpc ? "WARP-PER-CHUNK " : c.staged ? "cp.async staged" : "LDG registers  ", c.mma, c.N, c.nslot,
            c.relay == 1 ? "relay fence " : c.relay == 3 ? "3 relay warps" : c.relay == 0 ? "issuer fence" : "NO fence    ", (double)mx / (reps * (K / KC)), cudaGetErrorString(e));
   }
   return 0;
