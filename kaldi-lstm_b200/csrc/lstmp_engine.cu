@@ -252,7 +252,7 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     if (env_int("LSTMP_B200_TC_FWD", 1) && h->d.ngroups * h->d.ctas_per_group == sm_use) {
       FwdTcParams t{};
       size_t sz = 0;
-      if (fwd_tc_plan(C, R, S, sm_use, smem_limit, env_int("LSTMP_B200_TC_STAGED", 1), &t, &sz) && fwd_tc_set_smem_limit(sz) == cudaSuccess) {
+      if (fwd_tc_plan(C, R, S, sm_use, smem_limit, env_int("LSTMP_B200_TC_LOADER", env_int("LSTMP_B200_TC_STAGED", 1) ? 1 : 0), &t, &sz) && fwd_tc_set_smem_limit(sz) == cudaSuccess) {
         h->fwd_tc = true;
         t.stagger = env_int("LSTMP_B200_TC_STAGGER", 1);
         h->ftp = t;

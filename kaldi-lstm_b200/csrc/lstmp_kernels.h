@@ -76,7 +76,8 @@ struct FwdTcParams {
   int nctas, cpc, rpc;
   int n_g, n_p;                 // MMA N for the gate / projection products
   int nslot;                    // ring slots of [128 rows x 32 k]
-  int staged;                   // 1: cp.async landing slots + transform, 0: LDG.128 register prefetch (default)
+  int loader;                   // 1: cp.async landing slots + transform (default), 0: LDG.128 register prefetch,
+                                // 2: warp-per-chunk (opt-in, LSTMP_B200_TC_LOADER)
   int stagger;                  // 1: CTA j starts its K-chunk walk at chunk j mod nch (spreads the L2 requests)
   unsigned chunk_g, chunk_p;    // bytes of one 32-k tile of the stationary weight slices (SWIZZLE_128B)
   unsigned off_bg, off_bp, off_ring, slot_bytes, off_red, off_stage, ldred, off_cprev, off_peep, off_bars;
@@ -90,7 +91,7 @@ struct FwdTcParams {
   long long* dbg_stamps;
 };
 // false when the shape is not eligible (S > 64, C or R not a multiple of 32, slices do not fit)
-bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int staged, FwdTcParams* p, size_t* smem_bytes);
+bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int loader, FwdTcParams* p, size_t* smem_bytes);
 cudaError_t fwd_tc_set_smem_limit(size_t bytes);
 cudaError_t launch_fwd_tc(const FwdTcParams& p, size_t smem_bytes, cudaStream_t stream);
 

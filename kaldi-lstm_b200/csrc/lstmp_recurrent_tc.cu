@@ -28,8 +28,8 @@ namespace tcf {
 constexpr int KC = 32;                          // k per ring slot (4 MMAs of K = 8)
 constexpr int SLABS = KC / 4;                   // 16-byte K slabs per slot
 constexpr int LOADERS = 256;                    // warps 0-7
-constexpr int PF = 3;                           // STAGED: chunks of cp.async copies each loader thread keeps in flight
-constexpr int PFR = 4;                          // !STAGED: chunks of LDG.128 (register sets) in flight per loader thread
+constexpr int PF = 3;                           // LOADER 1: chunks of cp.async copies each loader thread keeps in flight
+constexpr int PFR = 4;                          // LOADER 0: chunks of LDG.128 (register sets) in flight per loader thread
 constexpr uint32_t SLOT_BYTES = 128 * 128;      // activation slot: 128 rows x 128 B, SWIZZLE_128B (lstmp_tc.cuh)
 constexpr int MAX_SLOTS = 8;
 constexpr uint32_t TMEM_COLS = 512;             // the whole TMEM: this CTA is alone on its SM
@@ -54,7 +54,7 @@ __device__ __forceinline__ void split4(float4 x, float4& h, float4& l) {
 // red[row*ldred + n] = D[row][n] + D[row][nh + n]  for the 128 stacked rows, n < nvalid.
 // X: [S x K] activations in global memory (row stride ld), written by other CTAs before the preceding group barrier.
 // Every thread of the CTA calls this; contains one __syncthreads.
-template <bool STAGED>
+template <int LOADER>  // 0: LDG.128 register prefetch, 1: cp.async landing slots (default), 2: warp-per-chunk
 __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const float* __restrict__ X, int ld, int K,
                                            uint32_t b_addr, uint32_t chunk_b, uint32_t idesc, uint32_t tmem_d, int nh,
                                            int nvalid, uint8_t* ring, uint64_t* full, uint64_t* ready,
@@ -72,7 +72,7 @@ __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const
 
   if (warp < 8) {
     // ------------------------------ loader / transform ---------------------------------------
-    // STAGED (default): stage 1 = cp.async.cg (LDGSTS, L2 -> raw landing slots, PF chunks in flight per thread,
+    // LOADER 1 (default): stage 1 = cp.async.cg (LDGSTS, L2 -> raw landing slots, PF chunks in flight per thread,
     // tracked by cp.async groups); stage 2 = each thread reads back ITS OWN two 16-byte units, splits them and stores
     // hi / lo into the UMMA tile.  The register-prefetch variant below measured 10 % slower (405 vs 367 us).
     const int S = p.S;
@@ -84,7 +84,7 @@ __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const
     const float* g1 = X + (size_t)r1 * ld + 4 * kc;
     // hi row r -> tile row r, lo row r -> tile row S + r (S % 8 == 0: same swizzle phase, offset S*128 bytes)
     const uint32_t so0 = tc::sw128_off(r0, kc), so1 = tc::sw128_off(r1, kc), lo_off = (uint32_t)S * 128;
-    if constexpr (STAGED) {
+    if constexpr (LOADER == 1) {
       uint8_t* my0 = stage + (size_t)u0 * 16;
       uint8_t* my1 = stage + (size_t)u1 * 16;
       const size_t stage_bytes = (size_t)nunits * 16;
@@ -136,8 +136,44 @@ __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const
           }
         }
       }
+    } else if constexpr (LOADER == 2) {
+      // Warp-per-chunk (LSTMP_B200_TC_LOADER=2, not yet validated on hardware): warp w loads, splits and stores the
+      // chunks c = w (mod 8) on its own -- lane l owns the 16-byte column l & 7 of rows (l >> 3) + 4 i -- and lane 0
+      // arrives on a full barrier of count 1, so up to nslot chunks are in progress at once.  In the two lockstep
+      // layouts every warp takes part in every chunk and a chunk cannot complete faster than one warp's dependent
+      // chain wait -> read back -> split -> wait for the slot -> store -> arrive.
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kcw = lane & 7, rl = lane >> 3;
+      for (int c = 0; c < nch; ++c) {
+        if ((c & 7) == warp) {
+          const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
+          const float* gsrc = X + (size_t)rl * ld + ce * KC + 4 * kcw;
+          float4 x[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = (rl + 4 * i < S) ? ld_cg_f4(gsrc + (size_t)(4 * i) * ld) : z;
+          if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+          uint8_t* st = ring + (size_t)slot * SLOT_BYTES;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = rl + 4 * i;
+            if (r < S) {
+              float4 h, l;
+              split4(x[i], h, l);
+              const uint32_t so = tc::sw128_off(r, kcw);
+              *reinterpret_cast<float4*>(st + so) = h;
+              *reinterpret_cast<float4*>(st + so + lo_off) = l;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&full[slot]);
+        }
+        if (++slot == (uint32_t)nslot) {
+          slot = 0;
+          ++use;
+        }
+      }
     } else {
-      // Register prefetch (LSTMP_B200_TC_STAGED=0): PFR chunks of LDG.128 (ld.global.cg) in flight per thread, no
+      // Register prefetch (LSTMP_B200_TC_LOADER=0): PFR chunks of LDG.128 (ld.global.cg) in flight per thread, no
       // landing slots -- a third less shared-memory traffic per chunk and room for a 6-slot ring, yet slower.
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       float4 v[PFR][2];
@@ -254,7 +290,7 @@ __device__ __forceinline__ void tc_product(const FwdTcParams& p, Pipe& ps, const
 }
 }  // namespace tcf
 
-template <bool STAGED>
+template <int LOADER>
 __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_constant__ FwdTcParams p) {
   using namespace tcf;
   extern __shared__ __align__(16) uint8_t smem_raw_tc[];
@@ -288,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_
 
   if (tid == 0) {
     for (int s = 0; s < p.nslot; ++s) {
-      mbar_init(&full[s], LOADERS / 32);
+      mbar_init(&full[s], LOADER == 2 ? 1 : LOADERS / 32);
       mbar_init(&ready[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -378,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_
       // r_{t-1}: carried state for the first frame of the chunk, else rbuf block tt
       const float* X = (tt == 0) ? p.state_r : p.rbuf + (size_t)tt * S * R;
       // gifo(t) += r(t-1) * W_gifo_r^T                                       (LPS.h:275)
-      tc_product<STAGED>(p, ps, X, R, R, bg_s, p.chunk_g, idesc_g, tmem_base + COL_G, 4 * cpc, 4 * nc, ring, full, ready, empty, accum,
+      tc_product<LOADER>(p, ps, X, R, R, bg_s, p.chunk_g, idesc_g, tmem_base + COL_G, 4 * cpc, 4 * nc, ring, full, ready, empty, accum,
                  red, stage);
       stamp(11);
       for (int idx = tid; idx < S * nc; idx += kThreads) {
@@ -421,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_
     stamp(21);
     // ================= phase 2: projection r(t) = m(t) * W_r_m^T for my columns (LPS.h:312) ==
     if (nr > 0) {
-      tc_product<STAGED>(p, ps, p.mbuf + (size_t)tt * S * C, C, C, bp_s, p.chunk_p, idesc_p, tmem_base + COL_P, rpc, nr, ring,
+      tc_product<LOADER>(p, ps, p.mbuf + (size_t)tt * S * C, C, C, bp_s, p.chunk_p, idesc_p, tmem_base + COL_P, rpc, nr, ring,
                  full, ready, empty, accum, red, stage);
       stamp(22);
       for (int idx = tid; idx < S * nr; idx += kThreads) {
@@ -455,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tc_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int staged, FwdTcParams* p, size_t* smem_bytes) {
+bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int loader, FwdTcParams* p, size_t* smem_bytes) {
   using namespace tcf;
   if (S < 8 || S > 64 || (S & 7)) return false;  // A tile: 2*S stacked rows <= 128 = the MMA's M; lo rows at row S
   if (C % KC || R % KC || nctas < 1) return false;
@@ -482,8 +518,9 @@ bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int staged, 
   p->off_ring = (unsigned)off;
   const int ldred = ((4 * cpc > rpc ? 4 * cpc : rpc) | 1);
   p->ldred = (unsigned)ldred;
-  p->staged = staged;
-  const size_t stage_total = staged ? (size_t)PF * S * SLABS * 16 : 0;
+  if (loader < 0 || loader > 2) return false;
+  p->loader = loader;
+  const size_t stage_total = loader == 1 ? (size_t)PF * S * SLABS * 16 : 0;
   const size_t tail = ((stage_total + 1023) & ~size_t(1023)) + (((size_t)S * cpc * 4 + 1023) & ~size_t(1023)) +
                       1024 /* peepholes */ + 1024 /* barriers + tmem slot */;
   const size_t reserve = 1024 /* base alignment */ + (size_t)static_smem_reserve();
@@ -512,10 +549,13 @@ cudaError_t fwd_tc_set_smem_limit(size_t bytes) {
   if (e != cudaSuccess) return e;
   dev &= 63;
   if (bytes <= cur[dev]) return cudaSuccess;
-  e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((const void*)lstmp_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)bytes);
   if (e != cudaSuccess) return e;
   cur[dev] = bytes;
@@ -525,7 +565,8 @@ cudaError_t fwd_tc_set_smem_limit(size_t bytes) {
 cudaError_t launch_fwd_tc(const FwdTcParams& p, size_t smem_bytes, cudaStream_t stream) {
   void* args[] = {(void*)&p};
   dim3 grid(p.nctas), block(kThreads);
-  const void* fn = p.staged ? (const void*)lstmp_fwd_tc_kernel<true> : (const void*)lstmp_fwd_tc_kernel<false>;
+  const void* fn = p.loader == 1 ? (const void*)lstmp_fwd_tc_kernel<1>
+                   : p.loader == 2 ? (const void*)lstmp_fwd_tc_kernel<2> : (const void*)lstmp_fwd_tc_kernel<0>;
   return cudaLaunchCooperativeKernel(fn, grid, block, args, smem_bytes, stream);
 }
 

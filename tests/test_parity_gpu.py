@@ -225,6 +225,27 @@ def test_copy_is_deep(klb, oracle_mod):
     assert np.abs(comp.GetParams()).max() > 0
 
 
+@pytest.mark.skipif(not os.environ.get("LSTMP_B200_EXPERIMENTAL"),
+                    reason="loader variants that have not been validated on hardware yet (set LSTMP_B200_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("loader", [0, 2])
+def test_tensor_core_forward_loader_variants(klb, oracle_blas, loader, monkeypatch):
+    """LSTMP_B200_TC_LOADER = 0 (register prefetch) / 2 (warp-per-chunk) against the oracle and the default loader."""
+    import torch
+    from parity_util import run_pair
+    monkeypatch.setenv("LSTMP_B200_TC_LOADER", str(loader))
+    for (I, C, R, S, T) in [(40, 256, 128, 64, 6), (16, 96, 64, 24, 5), (40, 800, 512, 64, 4)]:
+        _, comp, _ = run_pair(klb, oracle_blas, I=I, C=C, R=R, S=S, T=T, nchunks=2, scale=0.08, seed=60 + S,
+                              check_record=True, init_state=True)
+        assert comp.engine.info()["fwd_tensor_core"] == 1
+        x = torch.randn(T * S, I, device="cuda")
+        a = comp.Copy()
+        monkeypatch.setenv("LSTMP_B200_TC_LOADER", "1")
+        b = comp.Copy()
+        monkeypatch.setenv("LSTMP_B200_TC_LOADER", str(loader))
+        oa, ob = a.Propagate(x), b.Propagate(x)
+        assert (oa - ob).abs().max().item() <= 2e-5 * ob.abs().max().item()
+
+
 # ---- size-independent properties at BASELINE.json's full shapes -----------------------------
 def _full(klb, S=64, I=40, seed=0):
     import torch
