@@ -51,13 +51,13 @@ __device__ __forceinline__ float4 ldg_early(const float* p) {
 // hardware); a source stored with the M/N index contiguous ("MN-major", e.g. DGIFO^T for the weight
 // gradients) is transposed on the fly in registers: each thread owns a 4(k) x 4(mn) block, loads it with
 // four coalesced LDG.128 along mn and stores four 16-byte K-chunks, one per mn row.
-template <int ROWS, bool MN>
+template <int ROWS, bool MN, int NT = LOADERS>  // NT = threads that share one K block's tile (tid = index among them)
 struct Loader {
-  static constexpr int UNITS = ROWS * (BK / 4) / LOADERS;              // float4 units per thread (K-major source)
+  static constexpr int UNITS = ROWS * (BK / 4) / NT;              // float4 units per thread (K-major source)
   static constexpr int NBLK = (ROWS / 4) * (BK / 4);                    // 4x4 blocks per tile (MN-major source)
-  static constexpr int BPT = (NBLK + LOADERS - 1) / LOADERS;            // blocks per thread
+  static constexpr int BPT = (NBLK + NT - 1) / NT;            // blocks per thread
   static constexpr int NV = MN ? BPT * 4 : UNITS;                       // 16-byte units this thread owns per K block
-  static constexpr uint32_t RAW_BYTES = (uint32_t)NV * LOADERS * 16;    // raw landing slot of one K block
+  static constexpr uint32_t RAW_BYTES = (uint32_t)NV * NT * 16;    // raw landing slot of one K block
   float4 v[NV];
 
   // Stage 1: cp.async (LDGSTS, tracked by cp.async groups, NRAW K blocks in flight) of this thread's units of the K
@@ -69,7 +69,7 @@ struct Loader {
     if (!MN) {
 #pragma unroll
       for (int i = 0; i < UNITS; ++i) {
-        const int u = tid + i * LOADERS;
+        const int u = tid + i * NT;
         const int kc = u % (BK / 4), r = u / (BK / 4);
         const int gr = row0 + r, gk = k0 + 4 * kc;
         uint8_t* dst = raw + (size_t)u * 16;
@@ -80,13 +80,13 @@ struct Loader {
       // blocks of 4 k x 4 mn: block b -> mn-block mb = b % (ROWS/4), k-chunk kc = b / (ROWS/4)
 #pragma unroll
       for (int blk = 0; blk < BPT; ++blk) {
-        const int b = tid + blk * LOADERS;
+        const int b = tid + blk * NT;
         const int mb = b % (ROWS / 4), kc = b / (ROWS / 4);
         const int gr = row0 + 4 * mb;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int gk = k0 + 4 * kc + kk;
-          uint8_t* dst = raw + ((size_t)(blk * 4 + kk) * LOADERS + tid) * 16;
+          uint8_t* dst = raw + ((size_t)(blk * 4 + kk) * NT + tid) * 16;
           if (b < NBLK && gr < nrows && gk < K) cp_async16(dst, src + (size_t)gk * ld + gr);
           else *reinterpret_cast<float4*>(dst) = z;  // row kk of the block: 4 consecutive mn at k = 4kc+kk
         }
@@ -102,7 +102,7 @@ struct Loader {
     if (!MN) {
 #pragma unroll
       for (int i = 0; i < UNITS; ++i) {
-        const int u = tid + i * LOADERS;
+        const int u = tid + i * NT;
         const int kc = u % (BK / 4), r = u / (BK / 4);
         const int gr = row0 + r, gk = k0 + 4 * kc;
         v[i] = (gr < nrows && gk < K) ? ldg_early(src + (size_t)gr * ld + gk) : z;
@@ -110,7 +110,7 @@ struct Loader {
     } else {
 #pragma unroll
       for (int blk = 0; blk < BPT; ++blk) {
-        const int b = tid + blk * LOADERS;
+        const int b = tid + blk * NT;
         const int mb = b % (ROWS / 4), kc = b / (ROWS / 4);
         const int gr = row0 + 4 * mb;
 #pragma unroll
@@ -125,10 +125,10 @@ struct Loader {
   __device__ __forceinline__ void fetch(const uint8_t* raw, int tid) {
     if (!MN) {
 #pragma unroll
-      for (int i = 0; i < UNITS; ++i) v[i] = *reinterpret_cast<const float4*>(raw + (size_t)(tid + i * LOADERS) * 16);
+      for (int i = 0; i < UNITS; ++i) v[i] = *reinterpret_cast<const float4*>(raw + (size_t)(tid + i * NT) * 16);
     } else {
 #pragma unroll
-      for (int i = 0; i < BPT * 4; ++i) v[i] = *reinterpret_cast<const float4*>(raw + ((size_t)i * LOADERS + tid) * 16);
+      for (int i = 0; i < BPT * 4; ++i) v[i] = *reinterpret_cast<const float4*>(raw + ((size_t)i * NT + tid) * 16);
     }
   }
 
@@ -150,14 +150,14 @@ struct Loader {
     if (!MN) {
 #pragma unroll
       for (int i = 0; i < UNITS; ++i) {
-        const int u = tid + i * LOADERS;
+        const int u = tid + i * NT;
         const int kc = u % (BK / 4), r = u / (BK / 4);
         split_store(hi, lo, sw128_off(r, kc), v[i]);
       }
     } else {
 #pragma unroll
       for (int blk = 0; blk < BPT; ++blk) {
-        const int b = tid + blk * LOADERS;
+        const int b = tid + blk * NT;
         if (b >= NBLK) break;
         const int mb = b % (ROWS / 4), kc = b / (ROWS / 4);
         const float4 r0 = v[blk * 4 + 0], r1 = v[blk * 4 + 1], r2 = v[blk * 4 + 2], r3 = v[blk * 4 + 3];
@@ -180,8 +180,12 @@ struct Loader {
   }
 };
 
-template <int BN, bool A_MN, bool B_MN, bool STAGED>
+// MODE: 0 = LDG.128 register prefetch, all 8 loader warps on every K block; 1 = cp.async landing slots (default);
+//       2 = "ping-pong": two groups of 4 loader warps take alternate K blocks (register loads), so that two K blocks are
+//           in progress at once (opt-in, LSTMP_B200_GEMM_LOADER=2; not yet validated on hardware)
+template <int BN, bool A_MN, bool B_MN, int MODE>
 struct Smem {
+  static constexpr bool STAGED = (MODE == 1);
   static constexpr int NSTAGE = STAGED ? 2 : 3;                  // UMMA operand stages (hi/lo tiles of A and B)
   static constexpr uint32_t A_BYTES = tile_bytes(BM, false);
   static constexpr uint32_t B_BYTES = tile_bytes(BN, false);
@@ -191,12 +195,13 @@ struct Smem {
   static constexpr uint32_t TOTAL = NSTAGE * STAGE + (STAGED ? NRAW * RAW : 0) + 2048;  // + barriers, alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN, bool STAGED>
+template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float alpha,
                const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float beta,
                const float* __restrict__ bias, int k_per_split, float* __restrict__ split_ws) {
-  using SM = Smem<BN, A_MN, B_MN, STAGED>;
+  using SM = Smem<BN, A_MN, B_MN, MODE>;
+  constexpr bool STAGED = SM::STAGED;
   constexpr int NSTAGE = SM::NSTAGE;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // 1024-byte align the tile area (SWIZZLE_128B atoms)
@@ -235,7 +240,7 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], LOADERS / 32);
+      mbar_init(&full[s], MODE == 2 ? LOADERS / 64 : LOADERS / 32);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum_ready, 1);
@@ -255,7 +260,33 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
 
   if (warp < 8) {
     // =============================== loader / transform ==================================
-    if constexpr (STAGED) {
+    if constexpr (MODE == 2) {
+      // Two groups of 4 warps; group g loads, splits and stores the K blocks kb = g, g + 2, ... on its own (each thread
+      // owns twice as many units) and arrives with 4 warp arrivals.  With all 8 warps on every K block the block cannot
+      // complete faster than one warp's dependent chain load -> split -> wait for the stage -> store -> arrive.
+      constexpr int GT = LOADERS / 2;
+      const int grp = warp >> 2, gt = tid & (GT - 1);
+      Loader<BM, A_MN, GT> la;
+      Loader<BN, B_MN, GT> lb;
+      int kb = grp;
+      if (kb < nkb) {
+        la.load(A, lda, m0, M, kb * BK, K, gt);
+        lb.load(B, ldb, n0, N, kb * BK, K, gt);
+      }
+      for (; kb < nkb; kb += 2) {
+        const int s = kb % NSTAGE;
+        if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
+        uint8_t* st = tiles + (size_t)s * SM::STAGE;
+        la.store(st, st + SM::A_BYTES, gt);
+        lb.store(st + 2 * SM::A_BYTES, st + 2 * SM::A_BYTES + SM::B_BYTES, gt);
+        if (kb + 2 < nkb) {  // this group's next K block: in flight while the other group stores and the MMAs run
+          la.load(A, lda, m0, M, (kb + 2) * BK, K, gt);
+          lb.load(B, ldb, n0, N, (kb + 2) * BK, K, gt);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&full[s]);
+      }
+    } else if constexpr (STAGED) {
       Loader<BM, A_MN> la;
       Loader<BN, B_MN> lb;
   #pragma unroll
@@ -428,18 +459,18 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(float* __restrict__ 
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool STAGED>
+template <int BN, bool A_MN, bool B_MN, int MODE>
 static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
                               long long lda, const float* B, long long ldb, float beta, const float* bias,
                               cudaStream_t stream, float* ws, size_t ws_floats, int* nlaunch) {
-  using SM = Smem<BN, A_MN, B_MN, STAGED>;
+  using SM = Smem<BN, A_MN, B_MN, MODE>;
   *nlaunch = 1;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (!attr_set[dev & 63]) {
-    e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<BN, A_MN, B_MN, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute((const void*)gemm_tc_kernel<BN, A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SM::TOTAL);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
@@ -458,7 +489,7 @@ static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, floa
     const int kbs = (nkb + splits - 1) / splits;        // K blocks per split
     splits = (nkb + kbs - 1) / kbs;                      // drop empty tail splits
     grid.z = splits;
-    gemm_tc_kernel<BN, A_MN, B_MN, STAGED><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
+    gemm_tc_kernel<BN, A_MN, B_MN, MODE><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
                                                                        bias, kbs * BK, ws);
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return e2;
@@ -468,7 +499,7 @@ static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, floa
     *nlaunch = 2;
     return cudaGetLastError();
   }
-  gemm_tc_kernel<BN, A_MN, B_MN, STAGED><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
+  gemm_tc_kernel<BN, A_MN, B_MN, MODE><<<grid, block, SM::TOTAL, stream>>>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta,
                                                                      bias, 0, nullptr);
   return cudaGetLastError();
 }
@@ -493,17 +524,25 @@ cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float a
   if (!al16(C)) return cudaSuccess;
   *handled = true;
   const bool small_n = (N <= 64);
-  // operand loader variant: 1 = cp.async into raw landing slots (default; measured 43 vs 52 us on the weight-gradient
-  // GEMMs), 0 = LDG.128 into rotating register sets (LSTMP_B200_GEMM_STAGED=0)
-  static const bool staged = [] {
-    const char* v = getenv("LSTMP_B200_GEMM_STAGED");
-    return !(v && *v) || atoi(v) != 0;
+  // operand loader variant (LSTMP_B200_GEMM_LOADER): 1 = cp.async into raw landing slots (default; measured 43 vs 52 us
+  // on the weight-gradient GEMMs), 0 = LDG.128 into rotating register sets (also LSTMP_B200_GEMM_STAGED=0),
+  // 2 = ping-pong loader groups (opt-in, not yet validated on hardware)
+  static const int mode = [] {
+    const char* v = getenv("LSTMP_B200_GEMM_LOADER");
+    if (v && *v) {
+      const int m = atoi(v);
+      return (m >= 0 && m <= 2) ? m : 1;
+    }
+    const char* s = getenv("LSTMP_B200_GEMM_STAGED");
+    return (!(s && *s) || atoi(s) != 0) ? 1 : 0;
   }();
-#define LSTMP_TC_CASE(BN_, AMN_, BMN_)                                                                               \
-  return staged ? tc::launch_one<BN_, AMN_, BMN_, true>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, \
-                                                        ws, ws_floats, nlaunch)                                      \
-                : tc::launch_one<BN_, AMN_, BMN_, false>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, \
-                                                         ws, ws_floats, nlaunch)
+#define LSTMP_TC_CASE(BN_, AMN_, BMN_)                                                                                 \
+  return mode == 1 ? tc::launch_one<BN_, AMN_, BMN_, 1>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, \
+                                                        ws_floats, nlaunch)                                            \
+       : mode == 2 ? tc::launch_one<BN_, AMN_, BMN_, 2>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, \
+                                                        ws_floats, nlaunch)                                            \
+                   : tc::launch_one<BN_, AMN_, BMN_, 0>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, \
+                                                        ws_floats, nlaunch)
   if (small_n) {
     if (!a_mn && !b_mn) LSTMP_TC_CASE(64, false, false);
     if (!a_mn && b_mn) LSTMP_TC_CASE(64, false, true);
