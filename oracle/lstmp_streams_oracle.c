@@ -145,32 +145,34 @@ static void add_mat_dot_mat(real *D, int ldd, int rows, int cols, real alpha, co
 
 /* Kaldi VectorBase::Sigmoid (upstream kaldi-vector.cc): overflow-safe branches. */
 static inline real sigmoid1(real x) {
+  /* upstream writes the constants as double literals (`1.0 / (1.0 + Exp(-x))`): with Real = float the exp is
+   * expf, the division runs in double and is rounded once -- pinned against oracle/_ref (tests/test_ref_pin.py) */
 #if defined(ORACLE_IS_FLOAT)
-  if (x > 0) return (real)1 / ((real)1 + expf(-x));
+  if (x > 0.0) return (real)(1.0 / (1.0 + expf(-x)));
   real ex = expf(x);
-  return ex / (ex + (real)1);
+  return (real)(ex / (ex + 1.0));
 #else
-  if (x > 0) return (real)1 / ((real)1 + exp(-x));
+  if (x > 0.0) return 1.0 / (1.0 + exp(-x));
   real ex = exp(x);
-  return ex / (ex + (real)1);
+  return ex / (ex + 1.0);
 #endif
 }
-/* Kaldi VectorBase::Tanh (upstream kaldi-vector.cc). */
+/* Kaldi VectorBase::Tanh (upstream kaldi-vector.cc); same remark on the double literals. */
 static inline real tanh1(real x) {
 #if defined(ORACLE_IS_FLOAT)
-  if (x > 0) {
+  if (x > 0.0) {
     real inv_expx = expf(-x);
-    return (real)-1 + (real)2 / ((real)1 + inv_expx * inv_expx);
+    return (real)(-1.0 + 2.0 / (1.0 + inv_expx * inv_expx));
   }
   real expx = expf(x);
-  return (real)1 - (real)2 / ((real)1 + expx * expx);
+  return (real)(1.0 - 2.0 / (1.0 + expx * expx));
 #else
-  if (x > 0) {
+  if (x > 0.0) {
     real inv_expx = exp(-x);
-    return (real)-1 + (real)2 / ((real)1 + inv_expx * inv_expx);
+    return -1.0 + 2.0 / (1.0 + inv_expx * inv_expx);
   }
   real expx = exp(x);
-  return (real)1 - (real)2 / ((real)1 + expx * expx);
+  return 1.0 - 2.0 / (1.0 + expx * expx);
 #endif
 }
 static void sigmoid_mat(real *D, int ldd, int rows, int cols, const real *Sx, int lds) {
@@ -187,7 +189,7 @@ static void diff_sigmoid(real *D, int ldd, int rows, int cols, const real *val, 
   for (int i = 0; i < rows; i++)
     for (int j = 0; j < cols; j++) {
       real v = val[(size_t)i * ldv + j];
-      D[(size_t)i * ldd + j] = diff[(size_t)i * ldf + j] * v * ((real)1.0 - v);
+      D[(size_t)i * ldd + j] = (real)(diff[(size_t)i * ldf + j] * v * (1.0 - v)); /* double literal as in the reference */
     }
 }
 /* this = diff .* (1 - value^2)              -- kaldi-matrix.cc:2578-2593 */
@@ -196,7 +198,7 @@ static void diff_tanh(real *D, int ldd, int rows, int cols, const real *val, int
   for (int i = 0; i < rows; i++)
     for (int j = 0; j < cols; j++) {
       real v = val[(size_t)i * ldv + j];
-      D[(size_t)i * ldd + j] = diff[(size_t)i * ldf + j] * ((real)1.0 - v * v);
+      D[(size_t)i * ldd + j] = (real)(diff[(size_t)i * ldf + j] * (1.0 - (v * v))); /* double literal as in the reference */
     }
 }
 /* kaldi-matrix.cc:1868-1886 */

@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE: stands in for upstream Kaldi cudamatrix/cu-rand.h (not vendored by the reference); see ../kaldi-ref-shim.h
+#include "kaldi-ref-shim.h"

@@ -24,6 +24,13 @@ class XentOracle:
         # column 0 starting at -1e21, i.e. the FIRST column holding the row maximum (np.argmax has the same rule)
         return np.argmax(m, axis=1).astype(np.int32)
 
+    @staticmethod
+    def _cu_sum(m):
+        # CuMatrixBase::Sum (cu-matrix.cc:1984-1988): fp32 column sums accumulated row by row (AddRowSumMat), then
+        # Vector::Sum in double, returned as Real = float.  Pinned bit-for-bit against oracle/_ref.
+        col = np.add.reduce(np.ascontiguousarray(m, np.float32), axis=0, dtype=np.float32)
+        return float(np.float32(np.sum(col, dtype=np.float64)))
+
     def eval_masked(self, frame_mask_host, net_out, post):
         """frame_mask_host: [rows] float32 (1 = valid frame); net_out: [rows x num_pdf] softmax outputs;
         post: Kaldi `Posterior`, a list (per row) of lists of (pdf, weight).  Returns diff [rows x num_pdf]."""
@@ -48,8 +55,8 @@ class XentOracle:
         with np.errstate(divide="ignore", invalid="ignore"):
             xe = (np.log(net_out) * tgt) * mask[:, None]
             en = (np.log(tgt + np.float32(1e-20)) * tgt) * mask[:, None]
-        cross_entropy = -float(np.sum(xe, dtype=np.float64))
-        entropy = -float(np.sum(en, dtype=np.float64))
+        cross_entropy = -self._cu_sum(xe)
+        entropy = -self._cu_sum(en)
         self.loss += cross_entropy                                           # :138-142
         self.entropy += entropy
         self.correct += correct
