@@ -131,7 +131,10 @@ typedef struct {
   unsigned long long kernel_launches; /* kernels launched by this handle so far */
   int gemm_backend;                /* 0 = fp32 SIMT, 1 = tcgen05 3xTF32 */
   int weights_streamed;            /* 1: weight slices do not fit in shared memory; per-timestep GEMM path */
-  int fwd_tensor_core;             /* 1: the forward time loop runs on tcgen05 (num_stream <= 64), 0: FP32 FFMA */
+  int fwd_tensor_core;             /* forward time loop: 2 TMA-fed tcgen05 (bf16 hi/lo split, num_stream <= 64),
+                                      1 tcgen05 with register loaders (round 1), 0 FP32 FFMA */
+  int bwd_tensor_core;             /* backward time loop: 2 TMA-fed tcgen05 in clusters, 0 FP32 FFMA */
+  int bwd_ctas, bwd_cluster;       /* grid and cluster size of the backward tcgen05 kernel (0 when not used) */
 } lstmp_b200_info_t;
 int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* info);
 

@@ -67,7 +67,13 @@ struct lstmp_b200_engine {
   bool fwd_tc = false;
   FwdTcParams ftp{};
   size_t fwd_tc_smem = 0;
-  unsigned bar_base_tc = 0;
+  unsigned bar_base_tc = 0, bar_base_tcb = 0;
+  // TMA-fed tcgen05 time loops, forward and backward (lstmp_recurrent_tma.cu)
+  bool rec_tma = false;
+  FwdTmaParams ftm{};
+  BwdTmaParams btm{};
+  size_t fwd_tma_smem = 0, bwd_tma_smem = 0;
+  __nv_bfloat16 *rhl = nullptr, *mhl = nullptr, *dghl = nullptr, *drhl = nullptr;
   int T_last = 0;        // frames of the last propagate (0 = none)
   bool have_bwd = false; // a backpropagate record exists for T_last
   unsigned long long launches = 0;
@@ -168,6 +174,7 @@ extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
   for (float* b : bufs)
     if (b) cudaFree(b);
   if (h->bar) cudaFree(h->bar);
+  if (h->rhl) cudaFree(h->rhl);  // one allocation holds rhl | mhl | dghl | drhl
   for (auto& e : h->events) {  // timing enabled but never read back
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
@@ -249,7 +256,36 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
       delete h;
       return fail((int)e, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e));
     }
-    if (env_int("LSTMP_B200_TC_FWD", 1) && h->d.ngroups * h->d.ctas_per_group == sm_use) {
+    // default: TMA-fed tcgen05 loops in both directions (LSTMP_B200_REC=2); 1 = the round-1 tcgen05 forward loop with
+    // register loaders + FFMA backward; 0 = FFMA kernels
+    const int rec = env_int("LSTMP_B200_REC", 2);
+    if (rec >= 2) {
+      FwdTmaParams f{};
+      BwdTmaParams b{};
+      size_t fs = 0, bs = 0;
+      const int kp = env_int("LSTMP_B200_BWD_KP", 4);
+      bool okt = fwd_tma_plan(C, R, S, sm_use, smem_limit, &f, &fs);
+      // the grid of the backward kernel is the largest co-resident set of kp-CTA clusters; its shared-memory size
+      // depends on the grid through the slice sizes, so plan once with the optimistic grid and again with the real one
+      if (okt) okt = bwd_tma_plan(C, R, S, sm_use / kp * kp, kp, smem_limit, &b, &bs);
+      if (okt) okt = tma_set_smem_limits(fs, bs) == cudaSuccess;
+      if (okt) {
+        const int n = bwd_tma_max_ctas(kp, bs, sm_use);
+        okt = n >= kp && bwd_tma_plan(C, R, S, n, kp, smem_limit, &b, &bs) && tma_set_smem_limits(fs, bs) == cudaSuccess &&
+              bwd_tma_max_ctas(kp, bs, sm_use) >= n;
+      }
+      if (okt) {
+        h->rec_tma = true;
+        f.stagger = b.stagger = env_int("LSTMP_B200_TC_STAGGER", 1);
+        h->ftm = f;
+        h->btm = b;
+        h->fwd_tma_smem = fs;
+        h->bwd_tma_smem = bs;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    if (!h->rec_tma && rec >= 1 && env_int("LSTMP_B200_TC_FWD", 1) && h->d.ngroups * h->d.ctas_per_group == sm_use) {
       FwdTcParams t{};
       size_t sz = 0;
       if (fwd_tc_plan(C, R, S, sm_use, smem_limit, env_int("LSTMP_B200_TC_LOADER", env_int("LSTMP_B200_TC_STAGED", 1) ? 1 : 0), &t, &sz) && fwd_tc_set_smem_limit(sz) == cudaSuccess) {
@@ -293,6 +329,26 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
   if (e != cudaSuccess) {
     lstmp_b200_destroy(h);
     return fail((int)e, "barrier counters: %s", cudaGetErrorString(e));
+  }
+  if (h->rec_tma) {
+    const size_t n_r = (size_t)2 * S * R, n_m = (size_t)2 * S * C, n_dg = (size_t)2 * S * 4 * C;
+    const size_t total = (2 * n_r + n_m + n_dg) * sizeof(__nv_bfloat16);
+    e = cudaMalloc((void**)&h->rhl, total);
+    if (e == cudaSuccess) e = cudaMemset(h->rhl, 0, total);
+    if (e != cudaSuccess) {
+      lstmp_b200_destroy(h);
+      return fail(LSTMP_B200_ENOMEM, "hi/lo exchange arrays: %s", cudaGetErrorString(e));
+    }
+    h->mhl = h->rhl + n_r;
+    h->dghl = h->mhl + n_m;
+    h->drhl = h->dghl + n_dg;
+    ws += total;
+    if (make_hl_tensor_map(&h->ftm.tm_r, h->rhl, 2 * S, R, S) || make_hl_tensor_map(&h->ftm.tm_m, h->mhl, 2 * S, C, S) ||
+        make_hl_tensor_map(&h->btm.tm_dg, h->dghl, 2 * S, 4 * C, S) ||
+        make_hl_tensor_map(&h->btm.tm_dr, h->drhl, 2 * S, R, S)) {
+      lstmp_b200_destroy(h);
+      return fail(LSTMP_B200_EUNSUPPORTED, "cuTensorMapEncodeTiled failed for the hi/lo exchange arrays");
+    }
   }
   h->gemm_ws_floats = env_int("LSTMP_B200_SPLITK", 1) ? ((size_t)4 << 20) : 0;
   h->workspace_bytes = ws;
@@ -527,6 +583,34 @@ extern "C" int lstmp_b200_propagate(lstmp_b200_handle_t h, const float* in, size
     h->have_bwd = false;
     return 0;
   }
+  if (h->rec_tma) {
+    FwdTmaParams q = h->ftm;
+    q.I = I; q.C = C; q.R = R; q.S = S; q.T = T;
+    q.w_gifo_r = h->params + h->off_wr;
+    q.w_r_m = h->params + h->off_wm;
+    q.p_i = h->params + h->off_pi;
+    q.p_f = h->params + h->off_pf;
+    q.p_o = h->params + h->off_po;
+    q.gifo = h->gifo; q.cbuf = h->cbuf; q.hbuf = h->hbuf; q.mbuf = h->mbuf; q.rbuf = h->rbuf;
+    q.out = out;
+    q.ld_out = (long long)ld_out;
+    q.state_c = h->state_c;
+    q.state_r = h->state_r;
+    q.rhl = h->rhl; q.mhl = h->mhl;
+    q.bar = h->bar + (size_t)kMaxGroupsHost * kBarStride;
+    q.bar_base = h->bar_base_tc;
+    q.dbg = h->d.dbg;
+    q.dbg_stamps = h->dbg_stamps;
+    {
+      Timed tm(h, 1, st);
+      CUDA_TRY(launch_fwd_tma(q, h->fwd_tma_smem, st));
+    }
+    h->launches++;
+    h->bar_base_tc += (unsigned)(fwd_tma_barriers(T) * q.nctas);
+    h->T_last = T;
+    h->have_bwd = false;
+    return 0;
+  }
   if (h->fwd_tc) {
     FwdTcParams q = h->ftp;
     q.I = I; q.C = C; q.R = R; q.S = S; q.T = T;
@@ -624,6 +708,31 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
       CUDA_TRY(launch_streamed_small_grads(h->dgifo, h->cbuf, h->grads + h->off_bias, num_rows, S, C, st));
     }
     h->launches++;
+  } else if (h->rec_tma) {
+    BwdTmaParams q = h->btm;
+    q.I = I; q.C = C; q.R = R; q.S = S; q.T = T;
+    q.w_gifo_r = h->params + h->off_wr;
+    q.w_r_m = h->params + h->off_wm;
+    q.p_i = h->params + h->off_pi;
+    q.p_f = h->params + h->off_pf;
+    q.p_o = h->params + h->off_po;
+    q.gifo = h->gifo; q.cbuf = h->cbuf; q.hbuf = h->hbuf;
+    q.out_diff = out_diff;
+    q.ld_od = (long long)ld_od;
+    q.dgifo = h->dgifo; q.dr = h->dr;
+    q.g_small = h->grads + h->off_bias;  // bias / peephole gradients go straight into the arena (LPS.h:474-484)
+    q.dghl = h->dghl; q.drhl = h->drhl;
+    // its own counter: the forward and backward grids differ in size (clusters)
+    q.bar = h->bar + (size_t)kMaxGroupsHost * kBarStride + 64;
+    q.bar_base = h->bar_base_tcb;
+    q.dbg = h->d.dbg;
+    q.dbg_stamps = h->dbg_stamps;
+    {
+      Timed tm(h, 2, st);
+      CUDA_TRY(launch_bwd_tma(q, h->bwd_tma_smem, st));
+    }
+    h->launches++;
+    h->bar_base_tcb += (unsigned)(bwd_barriers(T) * q.nctas);
   } else {
   BwdParams p = h->bp;
   p.I = I; p.C = C; p.R = R; p.S = S; p.T = T;
@@ -707,13 +816,23 @@ extern "C" int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* inf
   info->max_frames = h->Tmax; info->sm_count = h->sm_count;
   info->ngroups = h->d.ngroups; info->ctas_per_group = h->d.ctas_per_group; info->streams_per_group = h->d.Sg;
   info->cells_per_cta = h->d.cpc; info->rcols_per_cta = h->d.rpc;
-  info->fwd_smem_bytes = h->fwd_tc ? h->fwd_tc_smem : h->fwd_smem;
-  info->bwd_smem_bytes = h->bwd_smem;
+  info->fwd_smem_bytes = h->rec_tma ? h->fwd_tma_smem : h->fwd_tc ? h->fwd_tc_smem : h->fwd_smem;
+  info->bwd_smem_bytes = h->rec_tma ? h->bwd_tma_smem : h->bwd_smem;
   info->workspace_bytes = h->workspace_bytes;
   info->kernel_launches = h->launches;
   info->gemm_backend = h->gemm_backend;
   info->weights_streamed = h->streamed ? 1 : 0;
-  info->fwd_tensor_core = h->fwd_tc ? 1 : 0;
+  info->fwd_tensor_core = h->rec_tma ? 2 : h->fwd_tc ? 1 : 0;
+  info->bwd_tensor_core = h->rec_tma ? 2 : 0;
+  if (h->rec_tma) {
+    info->ngroups = 1;
+    info->ctas_per_group = h->ftm.nctas;
+    info->streams_per_group = h->S;
+    info->cells_per_cta = h->ftm.cpc;
+    info->rcols_per_cta = h->ftm.rpc;
+    info->bwd_ctas = h->btm.nctas;
+    info->bwd_cluster = h->btm.kp;
+  }
   return 0;
 }
 

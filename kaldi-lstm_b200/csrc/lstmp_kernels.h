@@ -1,5 +1,7 @@
 // Internal (non-ABI) interface between the host engine and the sm_100a kernels.
 #pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 
@@ -94,6 +96,60 @@ struct FwdTcParams {
 bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int loader, FwdTcParams* p, size_t* smem_bytes);
 cudaError_t fwd_tc_set_smem_limit(size_t bytes);
 cudaError_t launch_fwd_tc(const FwdTcParams& p, size_t smem_bytes, cudaStream_t stream);
+
+// ---- TMA-fed tcgen05 time loops, forward and backward (lstmp_recurrent_tma.cu) --------------------------------
+// One stream group (all S <= 64 streams).  Activations cross the chip as bf16 hi/lo pairs written by their producer
+// ([2*S rows x K] global arrays: rows 0..S-1 hi, S..2S-1 lo) and are pulled into a SWIZZLE_128B shared-memory ring by
+// cp.async.bulk.tensor through the tensor maps below; the CTA's weight slice is the stationary B operand.
+struct FwdTmaParams {
+  int I, C, R, S, T;
+  int nctas, cpc, rpc;          // CTA j owns cells [j*cpc, +cpc) and r columns [j*rpc, +rpc)
+  int n_g, n_p;                 // MMA N of the gate / projection products
+  int nch_g, nch_p;             // 64-k chunks of the two contractions (K = R, K = C)
+  int nslot, stagger;
+  unsigned chunk_g, chunk_p;    // bytes of one 64-k tile of the stationary weight slices
+  unsigned off_bg, off_bp, off_ring, off_red, ldred, off_cprev, off_peep, off_bars;
+  const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
+  float *gifo, *cbuf, *hbuf, *mbuf, *rbuf, *out;
+  long long ld_out;
+  float *state_c, *state_r;
+  __nv_bfloat16 *rhl, *mhl;     // [2*S x R], [2*S x C]: hi/lo halves of the latest r / m
+  unsigned* bar;
+  unsigned bar_base;
+  int dbg;
+  long long* dbg_stamps;
+  CUtensorMap tm_r, tm_m;
+};
+struct BwdTmaParams {
+  int I, C, R, S, T;
+  int nctas, kp;                // grid = nctas CTAs in clusters of kp; cluster b owns d_r columns [b*rpb, +rpb)
+  int cpc, rpb;
+  int n_a, n_b;                 // MMA N of the d_r / d_m products
+  int nch_a, nch_b;             // 64-k chunks: K = 4C (split over the kp ranks of a cluster), K = R
+  int nslot, stagger;
+  unsigned chunk_a, chunk_b;
+  unsigned off_ba, off_bb, off_ring, off_red, ldred, off_part, off_dgn, off_dcn, off_acc7, off_peep, off_bars;
+  const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
+  const float *gifo, *cbuf, *hbuf;
+  const float* out_diff;
+  long long ld_od;
+  float *dgifo, *dr;
+  float* g_small;               // bias(4C) | peephole_i | peephole_f | peephole_o of the gradient arena
+  __nv_bfloat16 *dghl, *drhl;   // [2*S x 4C], [2*S x R]: hi/lo halves of the latest DGIFO / d_r
+  unsigned* bar;
+  unsigned bar_base;
+  int dbg;
+  long long* dbg_stamps;
+  CUtensorMap tm_dg, tm_dr;
+};
+bool fwd_tma_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTmaParams* p, size_t* smem_bytes);
+bool bwd_tma_plan(int C, int R, int S, int nctas, int kp, size_t smem_limit, BwdTmaParams* p, size_t* smem_bytes);
+int make_hl_tensor_map(void* out_map, const void* gptr, int rows, int K, int box_rows);
+cudaError_t tma_set_smem_limits(size_t fwd_bytes, size_t bwd_bytes);
+int bwd_tma_max_ctas(int kp, size_t smem_bytes, int max_ctas);
+cudaError_t launch_fwd_tma(const FwdTmaParams& p, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_bwd_tma(const BwdTmaParams& p, size_t smem_bytes, cudaStream_t stream);
+inline int fwd_tma_barriers(int T) { return 2 * T; }
 
 // C[M x N] = alpha * op(A) * op(B) + beta * C (+ bias[n] broadcast over rows), row-major with
 // leading dimensions; op(A) is M x K, op(B) is K x N.  tA/tB: 0 = as stored, 1 = transposed.

@@ -1,0 +1,858 @@
+// TMA-fed tcgen05 time loops for LstmProjectedStreams on sm_100a: forward (LPS.h:261-331) and the mirrored
+// truncated-BPTT backward (LPS.h:369-454), one persistent launch per chunk and direction, num_stream <= 64.
+// (LPS.h = google/nnet/bd-nnet-lstm-projected-streams.h of the reference.)
+//
+// Every per-timestep contraction is  D[128 x N] (TMEM, fp32) += A[128 x 16] * B[N x 16]^T  (tcgen05.mma.kind::f16,
+// bf16 operands).  FP32 fidelity comes from a two-piece bf16 split  x = hi + lo  (hi = bf16(x), lo = bf16(x - hi))
+// of BOTH operands, stacked instead of issued as extra instructions:
+//   A rows 0..S-1   = hi halves of the all-gathered activations of all streams, rows 64..64+S-1 = lo halves;
+//   B rows 0..n-1   = hi halves of the CTA's stationary weight slice,           rows n..2n-1    = lo halves;
+// one MMA yields all four cross products, result[s][j] = D[s][j] + D[s][n+j] + D[64+s][j] + D[64+s][n+j]
+// (relative error ~4e-6 end to end, tools/split_precision_study.py; the path's tolerance is 1e-4).
+//
+// The PRODUCER of an activation splits it: the CTA that computes r(t) / m(t) / d_r(t) / DGIFO(t) writes the hi and lo
+// bf16 halves to small global arrays ([2][S][K], L2-resident), and after the grid barrier every consumer pulls
+// [S rows x 64 k] boxes of both straight into a SWIZZLE_128B shared-memory ring with cp.async.bulk.tensor (TMA,
+// mbarrier expect_tx).  The operands reach shared memory through the async proxy: no loader warps, no register pass,
+// no generic stores, no proxy-fence relay -- one elected thread issues the copies, one issues the MMAs.
+//
+// Backward decomposition (the reason it differs from forward): d_r(t) = out_diff(t) + DGIFO(t+1) * W_gifo_r contracts
+// over K = 4C.  CTAs form clusters of kp; cluster b owns ~R/np columns of d_r, CTA rank a of the cluster contracts the
+// a-th K slice (TMA gather of 4C/kp columns of DGIFO(t+1) only) and the kp partial [S x R/np] blocks are summed through
+// distributed shared memory (a cluster barrier, not a grid barrier).  d_m(t) = d_r(t) * W_r_m and the derivative
+// chain run cell-sliced over all CTAs as in forward.  Two grid barriers per timestep in both directions.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include "lstmp_common.cuh"
+#include "lstmp_kernels.h"
+#include "lstmp_tc.cuh"
+
+namespace lstmp {
+
+namespace tm {
+constexpr int KC = 64;                       // bf16 k per ring slot row (128 bytes): 4 MMAs of K = 16
+constexpr uint32_t SLOT_BYTES = 128 * 128;   // [128 rows][128 B], SWIZZLE_128B; hi rows at 0, lo rows at row 64
+constexpr uint32_t LO_OFF = 64 * 128;
+constexpr int MAX_SLOTS = 8;
+constexpr uint32_t TMEM_COLS = 512;          // whole TMEM: the CTA is alone on its SM
+constexpr uint32_t COL_A = 0, COL_B = 256;   // accumulator columns of the first / second product of a timestep
+
+struct Pipe {
+  uint32_t cc;   // ring chunks produced / consumed so far (same sequence in every thread)
+  uint32_t acc;  // products finished so far (phase of the accumulator-ready barrier)
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_dst),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// kind::f16 with bf16 operands, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor):
+// D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  l = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+// 8 consecutive k of one weight row -> one 16-byte unit of the hi tile row and one of the lo tile row
+__device__ __forceinline__ void split8_store(const float* v, uint8_t* hi_dst, uint8_t* lo_dst) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[2 * i], h0, l0);
+    split_bf16(v[2 * i + 1], h1, l1);
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+// generic-proxy global stores <-> async-proxy (TMA) global reads: FENCE.VIEW.ASYNC.G only (the unqualified
+// fence.proxy.async adds a MEMBAR.ALL.GPU); gpu-scope ordering itself comes from the grid barrier's release / acquire
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
+
+struct Ring {
+  uint8_t* ring;
+  uint64_t *full, *empty, *accum;
+  int nslot;
+};
+
+// red[row*ldred + n] = D[row][n] + D[row][nh + n] for the 128 stacked rows, n < nvalid, where
+// D = A * B^T over K = 64*nch:  A = boxes [S x 64] (hi) / [S x 64] (lo) of the global [2*S x K] bf16 array behind
+// `tmap`, columns (kc0 + chunk)*64; B = the stationary tiles b_addr + chunk * chunk_b.  Chunks are walked in the
+// rotated order chunk = (c + rot) mod nch (order-independent sum up to fp32 rounding, fixed per CTA: bit-reproducible;
+// spreads the 148 CTAs' requests for the same lines over time).
+// Every thread of the CTA calls this (CTA-uniform arguments); contains one __syncthreads at the end.
+__device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, const CUtensorMap* tmap, int S, int kc0, int nch,
+                                            int rot, uint32_t b_addr, uint32_t chunk_b, uint32_t idesc, uint32_t tmem_d,
+                                            int nh, int nvalid, float* red, int ldred) {
+  // warp index through a shuffle: provably warp-uniform for ptxas (UMMA operands stay in uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int nslot = rg.nslot;
+  uint32_t slot = ps.cc % (uint32_t)nslot, use = ps.cc / (uint32_t)nslot;
+  if (warp == 8) {
+    // ------------------------------ TMA producer ---------------------------------------------
+    fence_async_global();  // other CTAs' generic-proxy stores (ordered by the grid barrier) before my async-proxy reads
+    const uint32_t ring_s = smem_u32(rg.ring);
+    const uint32_t bytes = (uint32_t)(2 * S * 128);
+    for (int c = 0; c < nch; ++c) {
+      if (use > 0) mbar_wait(&rg.empty[slot], (use - 1) & 1);
+      if (tc::elect_one()) {
+        const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
+        const uint32_t dst = ring_s + slot * SLOT_BYTES;
+        mbar_arrive_expect_tx(&rg.full[slot], bytes);
+        tma_load_2d(dst, tmap, (kc0 + ce) * KC, 0, &rg.full[slot]);
+        tma_load_2d(dst + LO_OFF, tmap, (kc0 + ce) * KC, S, &rg.full[slot]);
+      }
+      __syncwarp();
+      if (++slot == (uint32_t)nslot) {
+        slot = 0;
+        ++use;
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------ MMA issuer -----------------------------------------------
+    const uint32_t ring_s = smem_u32(rg.ring);
+    for (int c = 0; c < nch; ++c) {
+      mbar_wait(&rg.full[slot], use & 1);
+      tc::tc_fence_after();
+      {
+        // the whole warp runs the burst on warp-uniform operands; elect.sync predicates the instructions (lstmp_tc.cuh)
+        const uint32_t a0 = ring_s + slot * SLOT_BYTES;
+        const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
+        const uint32_t b0 = b_addr + (uint32_t)ce * chunk_b;
+#pragma unroll
+        for (int j = 0; j < KC / 16; ++j) {
+          // MMA j covers the 16-byte units 2j, 2j+1 of the 128-byte rows (K = 16 bf16 per instruction)
+          const uint64_t da = tc::make_desc_sw128(a0 + 32 * j);
+          const uint64_t db = tc::make_desc_sw128(b0 + 32 * j);
+          if (tc::elect_one()) mma_bf16(tmem_d, da, db, idesc, (c | j) ? 1u : 0u);
+        }
+        if (tc::elect_one()) {
+          tc::umma_commit(&rg.empty[slot]);             // frees the slot once these MMAs have read it
+          if (c == nch - 1) tc::umma_commit(rg.accum);  // accumulator complete
+        }
+      }
+      __syncwarp();
+      if (++slot == (uint32_t)nslot) {
+        slot = 0;
+        ++use;
+      }
+    }
+    tc::tc_fence_before();
+  } else if (warp < 4) {
+    // ---------------------------- accumulator -> shared memory -------------------------------
+    mbar_wait(rg.accum, ps.acc & 1);
+    tc::tc_fence_after();
+    const int row = warp * 32 + lane;  // TMEM lane = stacked activation row
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    float* rr = red + (size_t)row * ldred;
+    for (int c = 0; c < nvalid; c += 16) {
+      float a[16], b[16];
+      tc::tmem_ld16(taddr + (uint32_t)c, a);
+      tc::tmem_ld16(taddr + (uint32_t)(nh + c), b);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (c + q < nvalid) rr[c + q] = a[q] + b[q];
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  tc::tc_fence_after();
+  ps.cc += (uint32_t)nch;
+  ps.acc += 1;
+}
+
+__device__ __forceinline__ void store_hl(__nv_bfloat16* base, int S, size_t ld, int s, int col, float v) {
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  base[(size_t)s * ld + col] = h;
+  base[(size_t)(S + s) * ld + col] = l;
+}
+}  // namespace tm
+
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+__global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid_constant__ FwdTmaParams p) {
+  using namespace tm;
+  extern __shared__ __align__(16) uint8_t smem_raw_tma[];
+  // pointer arithmetic on the __shared__ array keeps the address space visible (LDS/STS instead of generic LD/ST)
+  uint8_t* base = smem_raw_tma + ((1024u - (smem_u32(smem_raw_tma) & 1023u)) & 1023u);
+  uint8_t* bg = base + p.off_bg;      // gate weight slice: nch_g tiles of [roundup8(8*cpc) rows][128 B] (hi rows, then lo)
+  uint8_t* bp = base + p.off_bp;      // projection slice:  nch_p tiles of [roundup8(2*rpc) rows][128 B]
+  float* red = reinterpret_cast<float*>(base + p.off_red);      // [128][ldred]
+  float* cprev = reinterpret_cast<float*>(base + p.off_cprev);  // [S*nc]
+  float* peep = reinterpret_cast<float*>(base + p.off_peep);    // [3][cpc]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + p.off_bars);
+  Ring rg;
+  rg.ring = base + p.off_ring;
+  rg.full = bars;
+  rg.empty = bars + MAX_SLOTS;
+  rg.accum = bars + 2 * MAX_SLOTS;
+  rg.nslot = p.nslot;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int j = blockIdx.x;
+  const int C = p.C, R = p.R, S = p.S, T = p.T;
+  const int cpc = p.cpc, rpc = p.rpc;
+  const int c0 = j * cpc;
+  const int nc = max(0, min(cpc, C - c0));  // my cells
+  const int r0 = j * rpc;
+  const int nr = max(0, min(rpc, R - r0));  // my projection outputs
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nslot; ++s) {
+      mbar_init(&rg.full[s], 1);
+      mbar_init(&rg.empty[s], 1);
+    }
+    mbar_init(rg.accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  // zero the operand area (weight tiles + ring): rows / k tails nobody fills must not hold NaN bit patterns
+  for (uint32_t o = (uint32_t)tid * 16; o < p.off_red; o += kThreads * 16)
+    *reinterpret_cast<uint4*>(base + o) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  // ---- stationary weight slices: split into bf16 hi / lo once per launch ----
+  if (nc > 0) {
+    const int rows = 4 * nc, nk8 = R >> 3;  // hi row = gate*nc + cl (gate order g,i,f,o: LPS.h:234-243)
+    for (int u = tid; u < rows * nk8; u += kThreads) {
+      const int row = u % rows, k8 = u / rows;
+      const int gate = row / nc, cl = row - gate * nc;
+      const float4* src = reinterpret_cast<const float4*>(p.w_gifo_r + (size_t)(gate * C + c0 + cl) * R) + 2 * k8;
+      const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
+      const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      uint8_t* t = bg + (size_t)(k8 >> 3) * p.chunk_g;
+      split8_store(v, t + tc::sw128_off(row, k8 & 7), t + tc::sw128_off(4 * cpc + row, k8 & 7));
+    }
+  }
+  if (nr > 0) {
+    const int nk8 = C >> 3;
+    for (int u = tid; u < nr * nk8; u += kThreads) {
+      const int row = u % nr, k8 = u / nr;
+      const float4* src = reinterpret_cast<const float4*>(p.w_r_m + (size_t)(r0 + row) * C) + 2 * k8;
+      const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
+      const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      uint8_t* t = bp + (size_t)(k8 >> 3) * p.chunk_p;
+      split8_store(v, t + tc::sw128_off(row, k8 & 7), t + tc::sw128_off(rpc + row, k8 & 7));
+    }
+  }
+
+  // ---- history: c_0 of my cells -> smem and cbuf block 0; r_0 of my columns -> rbuf block 0 + hi/lo (LPS.h:231) ----
+  for (int idx = tid; idx < S * nc; idx += kThreads) {
+    int s = idx / nc, cl = idx - s * nc;
+    float v = p.state_c[(size_t)s * C + c0 + cl];
+    cprev[idx] = v;
+    p.cbuf[(size_t)s * C + c0 + cl] = v;
+  }
+  for (int idx = tid; idx < S * nr; idx += kThreads) {
+    int s = idx / nr, n = idx - s * nr;
+    float v = p.state_r[(size_t)s * R + r0 + n];
+    p.rbuf[(size_t)s * R + r0 + n] = v;
+    store_hl(p.rhl, S, (size_t)R, s, r0 + n, v);
+  }
+  for (int cl = tid; cl < nc; cl += kThreads) {
+    peep[cl] = p.p_i[c0 + cl];
+    peep[cpc + cl] = p.p_f[c0 + cl];
+    peep[2 * cpc + cl] = p.p_o[c0 + cl];
+  }
+  tc::fence_async_smem();  // weight tiles (generic stores) -> UMMA
+  fence_async_global();    // r_0 hi/lo (generic stores) -> other CTAs' TMA
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t idesc_g = idesc_bf16(128, p.n_g), idesc_p = idesc_bf16(128, p.n_p);
+  const uint32_t bg_s = smem_u32(bg), bp_s = smem_u32(bp);
+  const int ldred = (int)p.ldred;
+  const int rot_g = p.stagger ? (int)(blockIdx.x % (unsigned)p.nch_g) : 0;
+  const int rot_p = p.stagger ? (int)(blockIdx.x % (unsigned)p.nch_p) : 0;
+
+  GroupBarrier gb;
+  gb.init(p.bar, p.bar_base, (unsigned)p.nctas, (p.dbg & 1) != 0);
+  stamp_begin((p.dbg & 4) && blockIdx.x == 0);
+  gb.sync();  // r_0 hi/lo of every CTA is in place
+  stamp(1);
+  Pipe ps{0u, 0u};
+
+  for (int tt = 0; tt < T; ++tt) {
+    stamp(10);
+    // ================= phase 1: gates + cell update for my cells ==========================
+    if (nc > 0) {
+      // this thread's first element's x-part pre-activations (input GEMM + bias): in flight during the product
+      float xg = 0.f, xi = 0.f, xf = 0.f, xo = 0.f;
+      if (tid < S * nc) {
+        int s = tid / nc, cl = tid - s * nc;
+        const float* gp = p.gifo + (size_t)(tt * S + s) * (4 * C) + c0 + cl;
+        xg = gp[0];
+        xi = gp[C];
+        xf = gp[2 * C];
+        xo = gp[3 * C];
+      }
+      // gifo(t) += r(t-1) * W_gifo_r^T                                       (LPS.h:275)
+      tma_product(ps, rg, &p.tm_r, S, 0, p.nch_g, rot_g, bg_s, p.chunk_g, idesc_g, tmem_base + COL_A, 4 * cpc, 4 * nc,
+                  red, ldred);
+      stamp(11);
+      for (int idx = tid; idx < S * nc; idx += kThreads) {
+        int s = idx / nc, cl = idx - s * nc;
+        size_t row = (size_t)tt * S + s;
+        float* gp = p.gifo + row * (4 * C) + c0 + cl;
+        if (idx >= kThreads) {
+          xg = gp[0];
+          xi = gp[C];
+          xf = gp[2 * C];
+          xo = gp[3 * C];
+        }
+        const float* rh = red + s * ldred + cl;         // hi-activation rows
+        const float* rl = red + (64 + s) * ldred + cl;  // lo-activation rows
+        float cp = cprev[idx];
+        float pi = peep[cl], pf = peep[cpc + cl], po = peep[2 * cpc + cl];
+        float ai = (rh[nc] + rl[nc]) + xi + cp * pi;          // :278  i += c(t-1) .* peephole_i_c
+        float af = (rh[2 * nc] + rl[2 * nc]) + xf + cp * pf;  // :281
+        float gi = sigmoidf_fast(ai);                         // :284
+        float gf = sigmoidf_fast(af);                         // :285
+        float gg = tanhf_fast((rh[0] + rl[0]) + xg);          // :288
+        float c = gg * gi + cp * gf;                          // :291-294
+        c = fminf(fmaxf(c, -kCellClip), kCellClip);           // :296-297
+        float h = tanhf_fast(c);                              // :300
+        float ao = (rh[3 * nc] + rl[3 * nc]) + xo + c * po;   // :303  (uses c(t), post-clip)
+        float go = sigmoidf_fast(ao);                         // :306
+        float m = h * go;                                     // :309
+        gp[0] = gg;
+        gp[C] = gi;
+        gp[2 * C] = gf;
+        gp[3 * C] = go;
+        p.cbuf[(row + S) * C + c0 + cl] = c;
+        p.hbuf[row * C + c0 + cl] = h;
+        p.mbuf[row * C + c0 + cl] = m;
+        store_hl(p.mhl, S, (size_t)C, s, c0 + cl, m);
+        cprev[idx] = c;
+      }
+      fence_async_global();
+    }
+    stamp(20);
+    gb.sync();
+    stamp(21);
+    // ================= phase 2: projection r(t) = m(t) * W_r_m^T for my columns (LPS.h:312) ==
+    if (nr > 0) {
+      tma_product(ps, rg, &p.tm_m, S, 0, p.nch_p, rot_p, bp_s, p.chunk_p, idesc_p, tmem_base + COL_B, rpc, nr, red,
+                  ldred);
+      stamp(22);
+      for (int idx = tid; idx < S * nr; idx += kThreads) {
+        int s = idx / nr, n = idx - s * nr;
+        float v = red[s * ldred + n] + red[(64 + s) * ldred + n];
+        size_t row = (size_t)tt * S + s;
+        p.rbuf[(row + S) * R + r0 + n] = v;
+        p.out[row * p.ld_out + r0 + n] = v;                         // :328
+        store_hl(p.rhl, S, (size_t)R, s, r0 + n, v);
+        if (tt == T - 1) p.state_r[(size_t)s * R + r0 + n] = v;     // :331
+      }
+      fence_async_global();
+    }
+    stamp(30);
+    if (tt + 1 < T) gb.sync();
+    stamp(31);
+  }
+  // prev_nnet_state_ <- last frame (LPS.h:331): c part
+  for (int idx = tid; idx < S * nc; idx += kThreads) {
+    int s = idx / nc, cl = idx - s * nc;
+    p.state_c[(size_t)s * C + c0 + cl] = cprev[idx];
+  }
+  stamp_flush(p.dbg_stamps);
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// =====================================================================================================================
+// backward
+// =====================================================================================================================
+__global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid_constant__ BwdTmaParams p) {
+  using namespace tm;
+  extern __shared__ __align__(16) uint8_t smem_raw_tma[];
+  uint8_t* base = smem_raw_tma + ((1024u - (smem_u32(smem_raw_tma) & 1023u)) & 1023u);
+  uint8_t* ba = base + p.off_ba;  // W_gifo_r[my K slice, my cluster's r columns]^T: tiles [roundup8(2*rpb) rows][128 B]
+  uint8_t* bb = base + p.off_bb;  // W_r_m[:, my cells]^T: nch_b tiles of [roundup8(2*cpc) rows][128 B]
+  float* red = reinterpret_cast<float*>(base + p.off_red);    // [128][ldred]
+  float* part = reinterpret_cast<float*>(base + p.off_part);  // [S][rpb] my partial d_r block (read by the cluster)
+  float* dgn = reinterpret_cast<float*>(base + p.off_dgn);    // [2][S*cpc]: d_i(t+1), d_f(t+1) of my cells
+  float* dcn = reinterpret_cast<float*>(base + p.off_dcn);    // [S*cpc]    d_c(t+1)
+  float* acc7 = reinterpret_cast<float*>(base + p.off_acc7);  // [S*cpc][7] running sums for bias / peephole gradients
+  float* peep = reinterpret_cast<float*>(base + p.off_peep);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + p.off_bars);
+  Ring rg;
+  rg.ring = base + p.off_ring;
+  rg.full = bars;
+  rg.empty = bars + MAX_SLOTS;
+  rg.accum = bars + 2 * MAX_SLOTS;
+  rg.nslot = p.nslot;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int j = blockIdx.x;
+  const int C = p.C, R = p.R, S = p.S, T = p.T;
+  const int cpc = p.cpc, rpb = p.rpb, kp = p.kp;
+  const int a = (int)cluster_ctarank();  // K slice of the d_r product
+  const int b = j / kp;                  // cluster index: r columns [n0, n0 + nn)
+  const int n0 = b * rpb;
+  const int nn = max(0, min(rpb, R - n0));
+  const int c0 = j * cpc;
+  const int nc = max(0, min(cpc, C - c0));  // my cells
+  // my K slice of the 4C contraction, in 64-column chunks
+  const int kbase = p.nch_a / kp, krem = p.nch_a % kp;
+  const int ks = a * kbase + min(a, krem);
+  const int nka = kbase + (a < krem ? 1 : 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nslot; ++s) {
+      mbar_init(&rg.full[s], 1);
+      mbar_init(&rg.empty[s], 1);
+    }
+    mbar_init(rg.accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  for (uint32_t o = (uint32_t)tid * 16; o < p.off_red; o += kThreads * 16)
+    *reinterpret_cast<uint4*>(base + o) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  // ---- stationary weight slices, transposed on the way in (B[n][k] = W[k][n]) and split into bf16 hi / lo ----
+  if (nn > 0) {
+    const int K4 = 4 * C;
+    for (int u = tid; u < nn * nka * 8; u += kThreads) {
+      const int n = u % nn, k8 = u / nn;  // k8: 8-k unit inside my slice
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = ks * KC + 8 * k8 + q;
+        v[q] = k < K4 ? __ldg(p.w_gifo_r + (size_t)k * R + n0 + n) : 0.f;
+      }
+      uint8_t* t = ba + (size_t)(k8 >> 3) * p.chunk_a;
+      split8_store(v, t + tc::sw128_off(n, k8 & 7), t + tc::sw128_off(rpb + n, k8 & 7));
+    }
+  }
+  if (nc > 0) {
+    for (int u = tid; u < nc * p.nch_b * 8; u += kThreads) {
+      const int n = u % nc, k8 = u / nc;
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = 8 * k8 + q;
+        v[q] = k < R ? __ldg(p.w_r_m + (size_t)k * C + c0 + n) : 0.f;
+      }
+      uint8_t* t = bb + (size_t)(k8 >> 3) * p.chunk_b;
+      split8_store(v, t + tc::sw128_off(n, k8 & 7), t + tc::sw128_off(cpc + n, k8 & 7));
+    }
+  }
+  for (int idx = tid; idx < 2 * S * cpc; idx += kThreads) dgn[idx] = 0.f;  // row-block T+1 is zero (LPS.h:352)
+  for (int idx = tid; idx < S * cpc; idx += kThreads) dcn[idx] = 0.f;
+  for (int idx = tid; idx < S * cpc * 7; idx += kThreads) acc7[idx] = 0.f;
+  for (int cl = tid; cl < nc; cl += kThreads) {
+    peep[cl] = p.p_i[c0 + cl];
+    peep[cpc + cl] = p.p_f[c0 + cl];
+    peep[2 * cpc + cl] = p.p_o[c0 + cl];
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t idesc_a = idesc_bf16(128, p.n_a), idesc_b = idesc_bf16(128, p.n_b);
+  const uint32_t ba_s = smem_u32(ba), bb_s = smem_u32(bb);
+  const int ldred = (int)p.ldred;
+  const int rot_a = (p.stagger && nka > 0) ? (int)((unsigned)b % (unsigned)nka) : 0;
+  const int rot_b = p.stagger ? (int)(blockIdx.x % (unsigned)p.nch_b) : 0;
+  const uint32_t part_s = smem_u32(part);
+
+  GroupBarrier gb;
+  gb.init(p.bar, p.bar_base, (unsigned)p.nctas, (p.dbg & 1) != 0);
+  stamp_begin((p.dbg & 8) && blockIdx.x == 0);
+  cluster_sync_all();  // every CTA of the cluster is running (its shared memory may be read from now on)
+  stamp(2);
+  Pipe ps{0u, 0u};
+  // my share of the cluster's [S x nn] d_r block in the reduction: streams s = a (mod kp)
+  const int nsh = (S - a + kp - 1) / kp;  // streams a, a+kp, ...
+
+  for (int tt = T - 1; tt >= 0; --tt) {
+    const bool have_next = (tt + 1 < T);
+    stamp(40);
+    // ============ phase A: d_r(t)[:, my columns] = out_diff(t) + DGIFO(t+1) * W_gifo_r            (LPS.h:367,391)
+    if (nn > 0) {
+      // out_diff of this thread's first reduction element: in flight during the product
+      float od = 0.f;
+      if (tid < nsh * nn) {
+        const int s = a + kp * (tid / nn), n = tid % nn;
+        od = p.out_diff[((size_t)tt * S + s) * p.ld_od + n0 + n];
+      }
+      if (have_next) {
+        if (nka > 0) {
+          tma_product(ps, rg, &p.tm_dg, S, ks, nka, rot_a, ba_s, p.chunk_a, idesc_a, tmem_base + COL_A, rpb, nn, red,
+                      ldred);
+          for (int idx = tid; idx < S * nn; idx += kThreads) {
+            const int s = idx / nn, n = idx - s * nn;
+            part[idx] = red[s * ldred + n] + red[(64 + s) * ldred + n];
+          }
+        } else {
+          for (int idx = tid; idx < S * nn; idx += kThreads) part[idx] = 0.f;
+        }
+        stamp(41);
+        cluster_sync_all();  // the kp partial blocks of this cluster are complete
+        stamp(42);
+      }
+      for (int li = tid; li < nsh * nn; li += kThreads) {
+        const int s = a + kp * (li / nn), n = li % nn;
+        const size_t row = (size_t)tt * S + s;
+        float v = (li < kThreads) ? od : p.out_diff[row * p.ld_od + n0 + n];
+        if (have_next) {
+          const uint32_t off = part_s + (uint32_t)((s * nn + n) * 4);
+          for (int q = 0; q < kp; ++q) v += ld_dsmem_f32(off, (uint32_t)q);  // fixed order: bit-reproducible
+        }
+        p.dr[row * R + n0 + n] = v;
+        store_hl(p.drhl, S, (size_t)R, s, n0 + n, v);
+      }
+      fence_async_global();
+    }
+    stamp(43);
+    gb.sync();
+    stamp(44);
+    // ============ phase B: d_m = d_r * W_r_m (my cells) (:408) + gate derivatives (:411-440)
+    if (nc > 0) {
+      // prefetch this thread's first element's activations while d_r is gathered and contracted
+      float yg = 0.f, yi = 0.f, yf = 0.f, yo = 0.f, yc = 0.f, ycp = 0.f, yh = 0.f, yfn = 0.f;
+      if (tid < S * nc) {
+        int s = tid / nc, cl = tid - s * nc;
+        size_t row = (size_t)tt * S + s;
+        const float* gp = p.gifo + row * (4 * C) + c0 + cl;
+        yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
+        yc = p.cbuf[(row + S) * C + c0 + cl];
+        ycp = p.cbuf[row * C + c0 + cl];
+        yh = p.hbuf[row * C + c0 + cl];
+        yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;
+      }
+      tma_product(ps, rg, &p.tm_dr, S, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b, tmem_base + COL_B, cpc, nc, red,
+                  ldred);
+      stamp(45);
+      for (int idx = tid; idx < S * nc; idx += kThreads) {
+        int s = idx / nc, cl = idx - s * nc;
+        size_t row = (size_t)tt * S + s;
+        if (idx >= kThreads) {
+          const float* gp = p.gifo + row * (4 * C) + c0 + cl;
+          yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
+          yc = p.cbuf[(row + S) * C + c0 + cl];
+          ycp = p.cbuf[row * C + c0 + cl];  // c(t-1): block tt
+          yh = p.hbuf[row * C + c0 + cl];
+          yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;  // f(t+1)
+        }
+        float pi = peep[cl], pf = peep[cpc + cl], po = peep[2 * cpc + cl];
+        float d_m = red[s * ldred + cl] + red[(64 + s) * ldred + cl];
+        float d_h = (d_m * yo) * (1.0f - yh * yh);            // :411-412
+        float d_o = (d_m * yh) * yo * (1.0f - yo);            // :415-416
+        float d_c = d_h;                                      // :424
+        d_c += dcn[idx] * yfn;                                // :425
+        d_c += dgn[idx] * pi;                                 // :426
+        d_c += dgn[S * cpc + idx] * pf;                       // :427
+        d_c += d_o * po;                                      // :428
+        float d_f = (d_c * ycp) * yf * (1.0f - yf);           // :431-432
+        float d_i = (d_c * yg) * yi * (1.0f - yi);            // :435-436
+        float d_g = (d_c * yi) * (1.0f - yg * yg);            // :439-440
+        float* dp = p.dgifo + row * (4 * C) + c0 + cl;
+        dp[0] = d_g;
+        dp[C] = d_i;
+        dp[2 * C] = d_f;
+        dp[3 * C] = d_o;
+        store_hl(p.dghl, S, (size_t)4 * C, s, c0 + cl, d_g);
+        store_hl(p.dghl, S, (size_t)4 * C, s, C + c0 + cl, d_i);
+        store_hl(p.dghl, S, (size_t)4 * C, s, 2 * C + c0 + cl, d_f);
+        store_hl(p.dghl, S, (size_t)4 * C, s, 3 * C + c0 + cl, d_o);
+        dgn[idx] = d_i;
+        dgn[S * cpc + idx] = d_f;
+        dcn[idx] = d_c;
+        float* a7 = acc7 + (size_t)idx * 7;
+        a7[0] += d_g;          // bias_corr_ column sums (:474)
+        a7[1] += d_i;
+        a7[2] += d_f;
+        a7[3] += d_o;
+        a7[4] += d_i * ycp;    // peephole_i_c_corr_  DI(t) .* C(t-1)  (:477)
+        a7[5] += d_f * ycp;    // peephole_f_c_corr_                  (:480)
+        a7[6] += d_o * yc;     // peephole_o_c_corr_  DO(t) .* C(t)    (:483)
+      }
+      fence_async_global();
+    }
+    stamp(46);
+    if (tt > 0) gb.sync();
+    stamp(47);
+  }
+  // bias / peephole gradients of my cells: sum over the streams in a fixed order, straight into the gradient arena
+  // (bias(4C) | peephole_i | peephole_f | peephole_o are contiguous there, LPS.h:162-189)
+  __syncthreads();
+  for (int q = tid; q < nc * 7; q += kThreads) {
+    int cl = q / 7, w = q - cl * 7;
+    float s7 = 0.f;
+    for (int s = 0; s < S; ++s) s7 += acc7[(size_t)(s * nc + cl) * 7 + w];
+    p.g_small[(size_t)w * C + c0 + cl] = s7;
+  }
+  stamp_flush(p.dbg_stamps);
+  tc::tc_fence_before();
+  cluster_sync_all();  // nobody exits while a peer may still read its partial block
+  if (warp == 8) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static size_t round1k(size_t b) { return (b + 1023) & ~size_t(1023); }
+
+bool fwd_tma_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTmaParams* p, size_t* smem_bytes) {
+  using namespace tm;
+  if (S < 1 || S > 64 || (C & 7) || (R & 7) || nctas < 1) return false;
+  const int cpc = (C + nctas - 1) / nctas, rpc = (R + nctas - 1) / nctas;
+  const int n_g = (8 * cpc + 15) & ~15, n_p = (2 * rpc + 15) & ~15;
+  if (n_g > 256 || n_p > 256) return false;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += round1k(bytes);
+    return (unsigned)o;
+  };
+  p->cpc = cpc;
+  p->rpc = rpc;
+  p->n_g = n_g;
+  p->n_p = n_p;
+  p->nctas = nctas;
+  p->nch_g = (R + KC - 1) / KC;
+  p->nch_p = (C + KC - 1) / KC;
+  p->chunk_g = (unsigned)(((8 * cpc + 7) & ~7) * 128);
+  p->chunk_p = (unsigned)(((2 * rpc + 7) & ~7) * 128);
+  p->off_bg = take((size_t)p->nch_g * p->chunk_g);
+  p->off_bp = take((size_t)p->nch_p * p->chunk_p);
+  // an MMA reads N (>= actual) weight rows per tile: the over-read of the last tiles lands in the ring that follows
+  // (finite values only -- the area is zeroed at kernel start -- and only into accumulator columns nobody reads)
+  p->off_ring = (unsigned)off;
+  const int ldred = ((4 * cpc > rpc ? 4 * cpc : rpc) | 1);
+  p->ldred = (unsigned)ldred;
+  const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)S * cpc * 4) + 1024 /* peepholes */ +
+                      1024 /* barriers + tmem slot */;
+  const size_t reserve = 1024 /* base alignment */ + (size_t)static_smem_reserve();
+  if (smem_limit < off + tail + reserve + (size_t)2 * SLOT_BYTES) return false;
+  int nslot = (int)((smem_limit - off - tail - reserve) / SLOT_BYTES);
+  if (nslot > MAX_SLOTS) nslot = MAX_SLOTS;
+  p->nslot = nslot;
+  off += (size_t)nslot * SLOT_BYTES;
+  p->off_red = take((size_t)128 * ldred * 4);
+  p->off_cprev = take((size_t)S * cpc * 4);
+  p->off_peep = take((size_t)3 * cpc * 4);
+  p->off_bars = take(256);
+  *smem_bytes = off + 1024;
+  return *smem_bytes + (size_t)static_smem_reserve() <= smem_limit;
+}
+
+bool bwd_tma_plan(int C, int R, int S, int nctas, int kp, size_t smem_limit, BwdTmaParams* p, size_t* smem_bytes) {
+  using namespace tm;
+  if (S < 1 || S > 64 || (C & 7) || (R & 7) || kp < 1 || kp > 8 || nctas < kp || nctas % kp) return false;
+  const int np = nctas / kp;
+  const int cpc = (C + nctas - 1) / nctas, rpb = (R + np - 1) / np;
+  const int n_a = (2 * rpb + 15) & ~15, n_b = (2 * cpc + 15) & ~15;
+  if (n_a > 256 || n_b > 256) return false;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += round1k(bytes);
+    return (unsigned)o;
+  };
+  p->nctas = nctas;
+  p->kp = kp;
+  p->cpc = cpc;
+  p->rpb = rpb;
+  p->n_a = n_a;
+  p->n_b = n_b;
+  p->nch_a = (4 * C + KC - 1) / KC;
+  p->nch_b = (R + KC - 1) / KC;
+  const int nka_max = (p->nch_a + kp - 1) / kp;
+  p->chunk_a = (unsigned)(((2 * rpb + 7) & ~7) * 128);
+  p->chunk_b = (unsigned)(((2 * cpc + 7) & ~7) * 128);
+  p->off_ba = take((size_t)nka_max * p->chunk_a);
+  p->off_bb = take((size_t)p->nch_b * p->chunk_b);
+  p->off_ring = (unsigned)off;
+  const int ldred = ((rpb > cpc ? rpb : cpc) | 1);
+  p->ldred = (unsigned)ldred;
+  const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)S * rpb * 4) + round1k((size_t)2 * S * cpc * 4) +
+                      round1k((size_t)S * cpc * 4) + round1k((size_t)S * cpc * 7 * 4) + 1024 + 1024;
+  const size_t reserve = 1024 + (size_t)static_smem_reserve();
+  if (smem_limit < off + tail + reserve + (size_t)2 * SLOT_BYTES) return false;
+  int nslot = (int)((smem_limit - off - tail - reserve) / SLOT_BYTES);
+  if (nslot > MAX_SLOTS) nslot = MAX_SLOTS;
+  p->nslot = nslot;
+  off += (size_t)nslot * SLOT_BYTES;
+  p->off_red = take((size_t)128 * ldred * 4);
+  p->off_part = take((size_t)S * rpb * 4);
+  p->off_dgn = take((size_t)2 * S * cpc * 4);
+  p->off_dcn = take((size_t)S * cpc * 4);
+  p->off_acc7 = take((size_t)S * cpc * 7 * 4);
+  p->off_peep = take((size_t)3 * cpc * 4);
+  p->off_bars = take(256);
+  *smem_bytes = off + 1024;
+  return *smem_bytes + (size_t)static_smem_reserve() <= smem_limit;
+}
+
+// [2*S rows x K] bf16 row-major array -> tensor map with [S rows x 64 k] boxes, 128-byte swizzle, zero fill outside
+// (the K tail of the last box).  cuTensorMapEncodeTiled is resolved through the runtime (no link against libcuda).
+int make_hl_tensor_map(void* out_map, const void* gptr, int rows, int K, int box_rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) return -1;
+    fn = (encode_fn)sym;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)tm::KC, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr),
+                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+cudaError_t tma_set_smem_limits(size_t fwd_bytes, size_t bwd_bytes) {
+  // per device and per function; several engines of different shapes may share the process: only ever raise it
+  static size_t cur_f[64] = {0}, cur_b[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  dev &= 63;
+  if (fwd_bytes > cur_f[dev]) {
+    e = cudaFuncSetAttribute((const void*)lstmp_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)fwd_bytes);
+    if (e != cudaSuccess) return e;
+    cur_f[dev] = fwd_bytes;
+  }
+  if (bwd_bytes > cur_b[dev]) {
+    e = cudaFuncSetAttribute((const void*)lstmp_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)bwd_bytes);
+    if (e != cudaSuccess) return e;
+    cur_b[dev] = bwd_bytes;
+  }
+  return cudaSuccess;
+}
+
+// Largest grid (multiple of kp, <= max_ctas) of kp-CTA clusters that is co-resident on the device.
+int bwd_tma_max_ctas(int kp, size_t smem_bytes, int max_ctas) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(max_ctas / kp * kp));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)kp;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, (const void*)lstmp_bwd_tma_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int n = ncl * kp;
+  if (n > max_ctas) n = max_ctas / kp * kp;
+  return n;
+}
+
+cudaError_t launch_fwd_tma(const FwdTmaParams& p, size_t smem_bytes, cudaStream_t stream) {
+  void* args[] = {(void*)&p};
+  dim3 grid(p.nctas), block(kThreads);
+  return cudaLaunchCooperativeKernel((const void*)lstmp_fwd_tma_kernel, grid, block, args, smem_bytes, stream);
+}
+
+cudaError_t launch_bwd_tma(const BwdTmaParams& p, size_t smem_bytes, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p.nctas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)p.kp;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  // co-residency of the whole grid is what the grid barrier needs: the grid was sized with
+  // cudaOccupancyMaxActiveClusters; the cooperative attribute makes the driver check it too.  Drivers that refuse
+  // cluster + cooperative in one launch get the plain cluster launch (same co-residency by construction).
+  static int coop_ok = 1;
+  if (coop_ok) {
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstmp_bwd_tma_kernel, p);
+    if (e == cudaSuccess) return e;
+    cudaGetLastError();
+    coop_ok = 0;
+  }
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, lstmp_bwd_tma_kernel, p);
+}
+
+}  // namespace lstmp

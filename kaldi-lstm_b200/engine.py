@@ -38,6 +38,7 @@ class Info(ctypes.Structure):
         ("fwd_smem_bytes", ctypes.c_size_t), ("bwd_smem_bytes", ctypes.c_size_t),
         ("workspace_bytes", ctypes.c_size_t), ("kernel_launches", ctypes.c_ulonglong),
         ("gemm_backend", ctypes.c_int), ("weights_streamed", ctypes.c_int), ("fwd_tensor_core", ctypes.c_int),
+        ("bwd_tensor_core", ctypes.c_int), ("bwd_ctas", ctypes.c_int), ("bwd_cluster", ctypes.c_int),
     ]
 
 

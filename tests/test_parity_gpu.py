@@ -111,33 +111,63 @@ def test_stream_group_decompositions(klb, oracle_blas, ngroups, monkeypatch):
     """The same maths under every work decomposition the engine can pick."""
     from parity_util import run_pair
     monkeypatch.setenv("LSTMP_B200_NGROUPS", str(ngroups))
-    monkeypatch.setenv("LSTMP_B200_TC_FWD", "0")  # the FP32 FFMA forward kernel under every decomposition
+    monkeypatch.setenv("LSTMP_B200_REC", "0")  # the FP32 FFMA kernels under every decomposition
     _, comp, _ = run_pair(klb, oracle_blas, I=40, C=256, R=128, S=64, T=6, nchunks=2, scale=0.08, seed=12 + ngroups)
     assert comp.engine.info()["ngroups"] == ngroups
     assert comp.engine.info()["fwd_tensor_core"] == 0
 
 
 @pytest.mark.parametrize("shape", [(40, 256, 128, 64, 6), (16, 96, 64, 24, 5), (8, 32, 32, 8, 3), (40, 800, 512, 64, 4),
-                                   (40, 800, 512, 32, 4)])
-def test_tensor_core_forward(klb, oracle_blas, shape, monkeypatch):
-    """The tcgen05 forward time loop (num_stream <= 64, cell/recur dims multiples of 32) against the oracle, with the
-    activation record checked, and against the FP32 FFMA forward kernel on the same inputs."""
+                                   (40, 800, 512, 32, 4), (8, 16, 8, 3, 4), (40, 800, 512, 5, 3)])
+def test_tma_tensor_core_loops(klb, oracle_blas, shape, monkeypatch):
+    """The TMA-fed tcgen05 time loops (num_stream <= 64, cell/recur dims multiples of 8), forward and backward, against
+    the oracle with both activation records checked, and against the FP32 FFMA kernels on the same inputs."""
     import torch
     from parity_util import run_pair
     I, C, R, S, T = shape
     _, comp, _ = run_pair(klb, oracle_blas, I=I, C=C, R=R, S=S, T=T, nchunks=3, scale=0.08, seed=40 + S,
                           check_record=True, init_state=True,
                           resets=[None, (np.arange(S) % 2 == 0).astype(np.int32), None])
-    assert comp.engine.info()["fwd_tensor_core"] == 1
+    info = comp.engine.info()
+    assert info["fwd_tensor_core"] == 2 and info["bwd_tensor_core"] == 2
     x = torch.randn(T * S, I, device="cuda")
+    od = torch.randn(T * S, R, device="cuda") * 0.1
     a = comp.Copy()
-    monkeypatch.setenv("LSTMP_B200_TC_FWD", "0")
+    monkeypatch.setenv("LSTMP_B200_REC", "0")
     b = comp.Copy()
-    assert a.engine.info()["fwd_tensor_core"] == 1 and b.engine.info()["fwd_tensor_core"] == 0
+    assert a.engine.info()["fwd_tensor_core"] == 2 and b.engine.info()["fwd_tensor_core"] == 0
+    assert b.engine.info()["bwd_tensor_core"] == 0
     oa, ob = a.Propagate(x), b.Propagate(x)
     assert (oa - ob).abs().max().item() <= 2e-5 * ob.abs().max().item()
     ra, rb = a.engine.get_record(False), b.engine.get_record(False)
     assert np.abs(ra - rb).max() <= 2e-5 * np.abs(rb).max()
+    da, db = a.Backpropagate(x, oa, od), b.Backpropagate(x, ob, od)
+    assert (da - db).abs().max().item() <= 2e-5 * db.abs().max().item()
+    ga, gb = a.engine.get_flat(2), b.engine.get_flat(2)
+    assert np.abs(ga - gb).max() <= 2e-5 * np.abs(gb).max()
+    ra, rb = a.engine.get_record(True), b.engine.get_record(True)
+    assert np.abs(ra - rb).max() <= 2e-5 * np.abs(rb).max()
+
+
+@pytest.mark.parametrize("kp", [1, 2, 4, 8])
+def test_backward_cluster_sizes(klb, oracle_blas, kp, monkeypatch):
+    """The backward kernel's d_r product is K-split over clusters of kp CTAs (partials summed through distributed shared
+    memory): same numbers for every cluster size."""
+    from parity_util import run_pair
+    monkeypatch.setenv("LSTMP_B200_BWD_KP", str(kp))
+    _, comp, _ = run_pair(klb, oracle_blas, I=40, C=256, R=128, S=64, T=6, nchunks=2, scale=0.08, seed=70 + kp,
+                          check_record=True)
+    info = comp.engine.info()
+    assert info["bwd_tensor_core"] == 2 and info["bwd_cluster"] == kp and info["bwd_ctas"] % kp == 0
+
+
+def test_tma_loops_few_ctas(klb, oracle_mod, monkeypatch):
+    """Few CTAs with many cells / columns each: multi-round elementwise loops, wide MMA N, one cluster."""
+    from parity_util import run_pair
+    monkeypatch.setenv("LSTMP_B200_MAX_CTAS", "6")
+    _, comp, _ = run_pair(klb, oracle_mod, I=16, C=96, R=40, S=20, T=4, nchunks=2, scale=0.2, seed=23, check_record=True)
+    info = comp.engine.info()
+    assert info["fwd_tensor_core"] == 2 and info["bwd_ctas"] == 4
 
 
 def test_few_ctas(klb, oracle_mod, monkeypatch):
@@ -223,27 +253,6 @@ def test_copy_is_deep(klb, oracle_mod):
     np.testing.assert_array_equal(a, b)  # same params AND same carried state
     twin.SetParams(np.zeros(twin.NumParams(), np.float32))
     assert np.abs(comp.GetParams()).max() > 0
-
-
-@pytest.mark.skipif(not os.environ.get("LSTMP_B200_EXPERIMENTAL"),
-                    reason="loader variants that have not been validated on hardware yet (set LSTMP_B200_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("loader", [0, 2])
-def test_tensor_core_forward_loader_variants(klb, oracle_blas, loader, monkeypatch):
-    """LSTMP_B200_TC_LOADER = 0 (register prefetch) / 2 (warp-per-chunk) against the oracle and the default loader."""
-    import torch
-    from parity_util import run_pair
-    monkeypatch.setenv("LSTMP_B200_TC_LOADER", str(loader))
-    for (I, C, R, S, T) in [(40, 256, 128, 64, 6), (16, 96, 64, 24, 5), (40, 800, 512, 64, 4)]:
-        _, comp, _ = run_pair(klb, oracle_blas, I=I, C=C, R=R, S=S, T=T, nchunks=2, scale=0.08, seed=60 + S,
-                              check_record=True, init_state=True)
-        assert comp.engine.info()["fwd_tensor_core"] == 1
-        x = torch.randn(T * S, I, device="cuda")
-        a = comp.Copy()
-        monkeypatch.setenv("LSTMP_B200_TC_LOADER", "1")
-        b = comp.Copy()
-        monkeypatch.setenv("LSTMP_B200_TC_LOADER", str(loader))
-        oa, ob = a.Propagate(x), b.Propagate(x)
-        assert (oa - ob).abs().max().item() <= 2e-5 * ob.abs().max().item()
 
 
 # ---- size-independent properties at BASELINE.json's full shapes -----------------------------
