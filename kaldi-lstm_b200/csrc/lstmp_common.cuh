@@ -146,12 +146,12 @@ __shared__ long long s_stamp_log[2 * kMaxStamps];
 __shared__ int s_stamp_n;
 __shared__ int s_stamp_on;
 __device__ __forceinline__ void stamp(int tag) {
-  if (threadIdx.x == 0 && s_stamp_on) {
-    int n = s_stamp_n;
+  // thread 0 everywhere; in the TMA-fed loops also the sync / producer thread (256) and the MMA issuer's lane 0 (288)
+  if ((threadIdx.x == 0 || ((threadIdx.x == 256 || threadIdx.x == 288) && tag >= 200)) && s_stamp_on) {
+    int n = atomicAdd(&s_stamp_n, 1);
     if (n < kMaxStamps) {
       s_stamp_log[2 * n] = tag;
       s_stamp_log[2 * n + 1] = clock64();
-      s_stamp_n = n + 1;
     }
   }
 }
@@ -164,7 +164,7 @@ __device__ __forceinline__ void stamp_begin(bool on) {
 __device__ __forceinline__ void stamp_flush(long long* dst) {
   if (threadIdx.x == 0 && s_stamp_on && dst) {
     long long base = dst[0];
-    int n = s_stamp_n;
+    int n = s_stamp_n < kMaxStamps ? s_stamp_n : kMaxStamps;
     for (int i = 0; i < n && base + i < 1024; ++i) {
       dst[2 + 2 * (base + i)] = s_stamp_log[2 * i];
       dst[3 + 2 * (base + i)] = s_stamp_log[2 * i + 1];

@@ -187,7 +187,8 @@ extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
     long long n = st[0];
     fprintf(stderr, "[lstmp_b200 stamps] %lld records (tag: delta cycles from previous)\n", n);
     for (long long i = 0; i < n && i < 1024; ++i)
-      fprintf(stderr, "  %4lld %8lld\n", st[2 + 2 * i], i ? st[3 + 2 * i] - st[1 + 2 * i] : 0LL);
+      fprintf(stderr, "  %4lld %8lld %10lld\n", st[2 + 2 * i], i ? st[3 + 2 * i] - st[1 + 2 * i] : 0LL,
+              st[3 + 2 * i] - st[3]);
     cudaFree(h->dbg_stamps);
   }
   delete h;
@@ -260,29 +261,35 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     // register loaders + FFMA backward; 0 = FFMA kernels
     const int rec = env_int("LSTMP_B200_REC", 2);
     if (rec >= 2) {
-      FwdTmaParams f{};
-      BwdTmaParams b{};
-      size_t fs = 0, bs = 0;
       const int kp = env_int("LSTMP_B200_BWD_KP", 4);
-      bool okt = fwd_tma_plan(C, R, S, sm_use, smem_limit, &f, &fs);
-      // the grid of the backward kernel is the largest co-resident set of kp-CTA clusters; its shared-memory size
-      // depends on the grid through the slice sizes, so plan once with the optimistic grid and again with the real one
-      if (okt) okt = bwd_tma_plan(C, R, S, sm_use / kp * kp, kp, smem_limit, &b, &bs);
-      if (okt) okt = tma_set_smem_limits(fs, bs) == cudaSuccess;
-      if (okt) {
-        const int n = bwd_tma_max_ctas(kp, bs, sm_use);
-        okt = n >= kp && bwd_tma_plan(C, R, S, n, kp, smem_limit, &b, &bs) && tma_set_smem_limits(fs, bs) == cudaSuccess &&
-              bwd_tma_max_ctas(kp, bs, sm_use) >= n;
-      }
-      if (okt) {
-        h->rec_tma = true;
-        f.stagger = b.stagger = env_int("LSTMP_B200_TC_STAGGER", 1);
-        h->ftm = f;
-        h->btm = b;
-        h->fwd_tma_smem = fs;
-        h->bwd_tma_smem = bs;
-      } else {
-        cudaGetLastError();
+      // stream groups: each group gathers only its own streams' activations (half the L2 -> SM traffic per CTA with
+      // two groups) at the price of twice the weight slice per CTA; the largest count whose slices fit, >= 16 streams
+      const int gforce = env_int("LSTMP_B200_TMA_GROUPS", 0);
+      for (int G = gforce > 0 ? gforce : 2; G >= 1 && !h->rec_tma; G = (gforce > 0 ? 0 : G - 1)) {
+        if (G > 2 || S % G || (G > 1 && gforce <= 0 && S / G < 16)) continue;  // barrier counters for <= 2 groups
+        FwdTmaParams f{};
+        BwdTmaParams b{};
+        size_t fs = 0, bs = 0;
+        bool okt = fwd_tma_plan(C, R, S, G, sm_use, smem_limit, &f, &fs);
+        // the backward grid is the largest co-resident set of kp-CTA clusters; its shared-memory size depends on the
+        // grid through the slice sizes, so plan with the optimistic grid first and again with the real one
+        if (okt) okt = bwd_tma_plan(C, R, S, G, sm_use, kp, smem_limit, &b, &bs);
+        if (okt) okt = tma_set_smem_limits(fs, bs) == cudaSuccess;
+        if (okt) {
+          const int n = bwd_tma_max_ctas(kp, bs, sm_use);
+          okt = n >= kp * G && bwd_tma_plan(C, R, S, G, n, kp, smem_limit, &b, &bs) &&
+                tma_set_smem_limits(fs, bs) == cudaSuccess && bwd_tma_max_ctas(kp, bs, sm_use) >= b.nctas;
+        }
+        if (okt) {
+          h->rec_tma = true;
+          f.stagger = b.stagger = env_int("LSTMP_B200_TC_STAGGER", 1);
+          h->ftm = f;
+          h->btm = b;
+          h->fwd_tma_smem = fs;
+          h->bwd_tma_smem = bs;
+        } else {
+          cudaGetLastError();
+        }
       }
     }
     if (!h->rec_tma && rec >= 1 && env_int("LSTMP_B200_TC_FWD", 1) && h->d.ngroups * h->d.ctas_per_group == sm_use) {
@@ -319,7 +326,7 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
       (rc = alloc_f(&h->scratch, h->streamed ? 4 : (size_t)h->d.ngroups * h->d.ctas_per_group * h->d.Sg * R, &ws)) ||
       (rc = alloc_f(&h->dm, h->streamed ? (size_t)S * C : 4, &ws)) ||
       (rc = alloc_f(&h->dc2, h->streamed ? (size_t)2 * S * C : 4, &ws)) ||
-      (rc = alloc_f(&h->small_grads, (size_t)h->d.ngroups * 7 * C, &ws)) ||
+      (rc = alloc_f(&h->small_grads, (size_t)kMaxGroupsHost * 7 * C, &ws)) ||
       (rc = alloc_f(&h->gemm_ws, (size_t)4 << 20, &ws))) {
     lstmp_b200_destroy(h);
     return rc;
@@ -343,9 +350,11 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     h->dghl = h->mhl + n_m;
     h->drhl = h->dghl + n_dg;
     ws += total;
-    if (make_hl_tensor_map(&h->ftm.tm_r, h->rhl, 2 * S, R, S) || make_hl_tensor_map(&h->ftm.tm_m, h->mhl, 2 * S, C, S) ||
-        make_hl_tensor_map(&h->btm.tm_dg, h->dghl, 2 * S, 4 * C, S) ||
-        make_hl_tensor_map(&h->btm.tm_dr, h->drhl, 2 * S, R, S)) {
+    const int Sg = h->ftm.Sg;
+    const int halves = 2 * h->ftm.G;
+    if (make_hl_tensor_map(&h->ftm.tm_r, h->rhl, halves, Sg, R) || make_hl_tensor_map(&h->ftm.tm_m, h->mhl, halves, Sg, C) ||
+        make_hl_tensor_map(&h->btm.tm_dg, h->dghl, halves, Sg, 4 * C) ||
+        make_hl_tensor_map(&h->btm.tm_dr, h->drhl, halves, Sg, R)) {
       lstmp_b200_destroy(h);
       return fail(LSTMP_B200_EUNSUPPORTED, "cuTensorMapEncodeTiled failed for the hi/lo exchange arrays");
     }
@@ -606,7 +615,7 @@ extern "C" int lstmp_b200_propagate(lstmp_b200_handle_t h, const float* in, size
       CUDA_TRY(launch_fwd_tma(q, h->fwd_tma_smem, st));
     }
     h->launches++;
-    h->bar_base_tc += (unsigned)(fwd_tma_barriers(T) * q.nctas);
+    h->bar_base_tc += (unsigned)(fwd_tma_barriers(T) * q.cpg);
     h->T_last = T;
     h->have_bwd = false;
     return 0;
@@ -720,10 +729,11 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
     q.out_diff = out_diff;
     q.ld_od = (long long)ld_od;
     q.dgifo = h->dgifo; q.dr = h->dr;
-    q.g_small = h->grads + h->off_bias;  // bias / peephole gradients go straight into the arena (LPS.h:474-484)
+    // bias / peephole gradients (LPS.h:474-484): straight into the arena, or per-group partials summed below
+    q.g_small = q.G == 1 ? h->grads + h->off_bias : h->small_grads;
     q.dghl = h->dghl; q.drhl = h->drhl;
     // its own counter: the forward and backward grids differ in size (clusters)
-    q.bar = h->bar + (size_t)kMaxGroupsHost * kBarStride + 64;
+    q.bar = h->bar + (size_t)kMaxGroupsHost * kBarStride + 128;  // forward: groups at +0, +64
     q.bar_base = h->bar_base_tcb;
     q.dbg = h->d.dbg;
     q.dbg_stamps = h->dbg_stamps;
@@ -732,7 +742,12 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
       CUDA_TRY(launch_bwd_tma(q, h->bwd_tma_smem, st));
     }
     h->launches++;
-    h->bar_base_tcb += (unsigned)(bwd_barriers(T) * q.nctas);
+    h->bar_base_tcb += (unsigned)(bwd_barriers(T) * q.cpg);
+    if (q.G > 1) {
+      Timed tm(h, 5, st);
+      CUDA_TRY(launch_small_grads(h->grads + h->off_bias, h->small_grads, q.G, 7 * C, st));
+      h->launches++;
+    }
   } else {
   BwdParams p = h->bp;
   p.I = I; p.C = C; p.R = R; p.S = S; p.T = T;
@@ -825,9 +840,9 @@ extern "C" int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* inf
   info->fwd_tensor_core = h->rec_tma ? 2 : h->fwd_tc ? 1 : 0;
   info->bwd_tensor_core = h->rec_tma ? 2 : 0;
   if (h->rec_tma) {
-    info->ngroups = 1;
-    info->ctas_per_group = h->ftm.nctas;
-    info->streams_per_group = h->S;
+    info->ngroups = h->ftm.G;
+    info->ctas_per_group = h->ftm.cpg;
+    info->streams_per_group = h->ftm.Sg;
     info->cells_per_cta = h->ftm.cpc;
     info->rcols_per_cta = h->ftm.rpc;
     info->bwd_ctas = h->btm.nctas;

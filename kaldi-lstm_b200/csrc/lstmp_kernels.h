@@ -103,7 +103,8 @@ cudaError_t launch_fwd_tc(const FwdTcParams& p, size_t smem_bytes, cudaStream_t 
 // cp.async.bulk.tensor through the tensor maps below; the CTA's weight slice is the stationary B operand.
 struct FwdTmaParams {
   int I, C, R, S, T;
-  int nctas, cpc, rpc;          // CTA j owns cells [j*cpc, +cpc) and r columns [j*rpc, +rpc)
+  int G, Sg, cpg;               // stream groups (own barrier each), streams per group, CTAs per group
+  int nctas, cpc, rpc;          // CTA j of a group owns cells [j*cpc, +cpc) and r columns [j*rpc, +rpc)
   int n_g, n_p;                 // MMA N of the gate / projection products
   int nch_g, nch_p;             // 64-k chunks of the two contractions (K = R, K = C)
   int nslot, stagger;
@@ -113,7 +114,7 @@ struct FwdTmaParams {
   float *gifo, *cbuf, *hbuf, *mbuf, *rbuf, *out;
   long long ld_out;
   float *state_c, *state_r;
-  __nv_bfloat16 *rhl, *mhl;     // [2*S x R], [2*S x C]: hi/lo halves of the latest r / m
+  __nv_bfloat16 *rhl, *mhl;     // [G][2][Sg] x R, x C: hi/lo halves of the latest r / m
   unsigned* bar;
   unsigned bar_base;
   int dbg;
@@ -122,29 +123,30 @@ struct FwdTmaParams {
 };
 struct BwdTmaParams {
   int I, C, R, S, T;
-  int nctas, kp;                // grid = nctas CTAs in clusters of kp; cluster b owns d_r columns [b*rpb, +rpb)
+  int G, Sg, cpg;               // stream groups, streams per group, CTAs per group (a multiple of kp)
+  int nctas, kp;                // grid = nctas CTAs in clusters of kp; cluster b of a group owns d_r columns [b*rpb, +rpb)
   int cpc, rpb;
   int n_a, n_b;                 // MMA N of the d_r / d_m products
   int nch_a, nch_b;             // 64-k chunks: K = 4C (split over the kp ranks of a cluster), K = R
   int nslot, stagger;
   unsigned chunk_a, chunk_b;
-  unsigned off_ba, off_bb, off_ring, off_red, ldred, off_part, off_dgn, off_dcn, off_acc7, off_peep, off_bars;
+  unsigned off_ba, off_bb, off_ring, off_red, ldred, off_dgn, off_dcn, off_acc7, off_peep, off_bars;
   const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
   const float *gifo, *cbuf, *hbuf;
   const float* out_diff;
   long long ld_od;
   float *dgifo, *dr;
-  float* g_small;               // bias(4C) | peephole_i | peephole_f | peephole_o of the gradient arena
-  __nv_bfloat16 *dghl, *drhl;   // [2*S x 4C], [2*S x R]: hi/lo halves of the latest DGIFO / d_r
+  float* g_small;               // [G][7C] bias(4C) | peephole_i | peephole_f | peephole_o (G == 1: the gradient arena)
+  __nv_bfloat16 *dghl, *drhl;   // [G][2][Sg] x 4C, x R: hi/lo halves of the latest DGIFO / d_r
   unsigned* bar;
   unsigned bar_base;
   int dbg;
   long long* dbg_stamps;
   CUtensorMap tm_dg, tm_dr;
 };
-bool fwd_tma_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTmaParams* p, size_t* smem_bytes);
-bool bwd_tma_plan(int C, int R, int S, int nctas, int kp, size_t smem_limit, BwdTmaParams* p, size_t* smem_bytes);
-int make_hl_tensor_map(void* out_map, const void* gptr, int rows, int K, int box_rows);
+bool fwd_tma_plan(int C, int R, int S, int G, int nctas, size_t smem_limit, FwdTmaParams* p, size_t* smem_bytes);
+bool bwd_tma_plan(int C, int R, int S, int G, int nctas, int kp, size_t smem_limit, BwdTmaParams* p, size_t* smem_bytes);
+int make_hl_tensor_map(void* out_map, const void* gptr, int halves, int Sg, int K);
 cudaError_t tma_set_smem_limits(size_t fwd_bytes, size_t bwd_bytes);
 int bwd_tma_max_ctas(int kp, size_t smem_bytes, int max_ctas);
 cudaError_t launch_fwd_tma(const FwdTmaParams& p, size_t smem_bytes, cudaStream_t stream);

@@ -33,8 +33,8 @@ namespace lstmp {
 
 namespace tm {
 constexpr int KC = 64;                       // bf16 k per ring slot row (128 bytes): 4 MMAs of K = 16
-constexpr uint32_t SLOT_BYTES = 128 * 128;   // [128 rows][128 B], SWIZZLE_128B; hi rows at 0, lo rows at row 64
-constexpr uint32_t LO_OFF = 64 * 128;
+constexpr uint32_t SLOT_BYTES = 128 * 128;   // [128 rows][128 B], SWIZZLE_128B; hi rows at 0, lo rows at row Sg
+constexpr int NPROD = 3;                     // TMA producer warps (8, 10, 11): chunk c is issued by producer c mod 3
 constexpr int MAX_SLOTS = 8;
 constexpr uint32_t TMEM_COLS = 512;          // whole TMEM: the CTA is alone on its SM
 constexpr uint32_t COL_A = 0, COL_B = 256;   // accumulator columns of the first / second product of a timestep
@@ -44,11 +44,12 @@ struct Pipe {
   uint32_t acc;  // products finished so far (phase of the accumulator-ready barrier)
 };
 
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
           "r"(smem_dst),
-      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
@@ -109,48 +110,92 @@ __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy
 
 struct Ring {
   uint8_t* ring;
-  uint64_t *full, *empty, *accum;
+  uint64_t *full, *empty, *accum, *gridok;
   int nslot;
 };
 
+// Grid barrier between the co-resident CTAs of one stream group, split into arrive / wait and run by ONE thread per
+// CTA (lane 0 of the TMA producer warp): only the TMA reads depend on other CTAs' data, so nobody else ever waits for
+// the grid -- the other warps are gated by the mbarrier chain full -> MMA -> accum.  Same monotonic counter as
+// GroupBarrier (lstmp_common.cuh): barrier k is complete when counter - base >= k * nctas.  A CTA must wait for
+// barrier k before it arrives at barrier k+1 (the same thread does both, in program order).
+struct GridSync {
+  unsigned* counter;
+  unsigned target;
+  unsigned nctas;
+  bool off;
+  // after a __syncthreads that ordered the CTA's hi/lo stores (each followed by fence.proxy.async.global)
+  __device__ __forceinline__ void arrive() {
+    target += nctas;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+    stamp(200);
+  }
+  __device__ __forceinline__ void wait() {
+    if (!off) {
+      // acquire LOADS, not relaxed loads + fence.acq_rel.gpu: the fence also waits for this thread's own record
+      // stores still in flight (measured ~1200 cycles per barrier); one polling thread per CTA makes the L1
+      // invalidate that comes with every acquire load harmless
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(counter) : "memory");
+      } while (static_cast<int>(v - target) < 0);
+      stamp(201);
+    }
+    fence_async_global();  // other CTAs' generic-proxy stores before my async-proxy (TMA) reads
+    stamp(202);
+  }
+};
+constexpr int kProducerWarp = 8, kIssuerWarp = 9;
+__device__ __forceinline__ bool is_sync_thread() { return threadIdx.x == kProducerWarp * 32; }
+
 // red[row*ldred + n] = D[row][n] + D[row][nh + n] for the 128 stacked rows, n < nvalid, where
-// D = A * B^T over K = 64*nch:  A = boxes [S x 64] (hi) / [S x 64] (lo) of the global [2*S x K] bf16 array behind
-// `tmap`, columns (kc0 + chunk)*64; B = the stationary tiles b_addr + chunk * chunk_b.  Chunks are walked in the
-// rotated order chunk = (c + rot) mod nch (order-independent sum up to fp32 rounding, fixed per CTA: bit-reproducible;
-// spreads the 148 CTAs' requests for the same lines over time).
+// D = A * B^T over K = 64*nch:  A = boxes [2 halves x Sg x 64] of the global bf16 array behind `tmap` (halves half0 =
+// hi, half0 + 1 = lo), columns (kc0 + chunk)*64; B = the stationary tiles b_addr + chunk * chunk_b.  Chunks are walked in
+// the rotated order chunk = (c + rot) mod nch (order-independent sum up to fp32 rounding, fixed per CTA:
+// bit-reproducible; spreads the CTAs' requests for the same lines over time).  grid_wait: the operand was written by
+// other CTAs before the grid barrier this CTA last arrived at -- the producer waits for it before its first copy.
 // Every thread of the CTA calls this (CTA-uniform arguments); contains one __syncthreads at the end.
-__device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, const CUtensorMap* tmap, int S, int kc0, int nch,
-                                            int rot, uint32_t b_addr, uint32_t chunk_b, uint32_t idesc, uint32_t tmem_d,
-                                            int nh, int nvalid, float* red, int ldred) {
+__device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& gs, bool grid_wait,
+                                            const CUtensorMap* tmap, int Sg, int half0, int kc0, int nch, int rot,
+                                            uint32_t b_addr, uint32_t chunk_b, uint32_t idesc, uint32_t tmem_d, int nh,
+                                            int nvalid, float* red, int ldred) {
   // warp index through a shuffle: provably warp-uniform for ptxas (UMMA operands stay in uniform registers)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int nslot = rg.nslot;
   uint32_t slot = ps.cc % (uint32_t)nslot, use = ps.cc / (uint32_t)nslot;
-  if (warp == 8) {
-    // ------------------------------ TMA producer ---------------------------------------------
-    fence_async_global();  // other CTAs' generic-proxy stores (ordered by the grid barrier) before my async-proxy reads
-    const uint32_t ring_s = smem_u32(rg.ring);
-    const uint32_t bytes = (uint32_t)(2 * S * 128);
-    for (int c = 0; c < nch; ++c) {
-      if (use > 0) mbar_wait(&rg.empty[slot], (use - 1) & 1);
-      if (tc::elect_one()) {
+  const int prod = warp == kProducerWarp ? 0 : warp == kProducerWarp + 2 ? 1 : warp == kProducerWarp + 3 ? 2 : -1;
+  if (prod >= 0) {
+    // ------------------------------ TMA producers --------------------------------------------
+    // One 3-D box [2 halves][Sg rows][64 k] = one copy per chunk.  A copy costs its issuing thread ~150-200 cycles
+    // whatever its size (measured: 380 cycles per chunk with two 2-D copies from one thread), so the chunks are dealt
+    // round-robin to three threads in three warps.
+    if (lane == 0) {
+      if (grid_wait) {
+        if (prod == 0) {
+          gs.wait();
+          tc::mbar_arrive(rg.gridok);
+        } else {
+          mbar_wait(rg.gridok, ps.acc & 1);
+        }
+      }
+      const uint32_t ring_s = smem_u32(rg.ring);
+      const uint32_t bytes = (uint32_t)(2 * Sg * 128);
+      for (int c = prod; c < nch; c += NPROD) {
+        const uint32_t idx = ps.cc + (uint32_t)c, sl = idx % (uint32_t)nslot, us = idx / (uint32_t)nslot;
+        if (us > 0) mbar_wait(&rg.empty[sl], (us - 1) & 1);
         const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
-        const uint32_t dst = ring_s + slot * SLOT_BYTES;
-        mbar_arrive_expect_tx(&rg.full[slot], bytes);
-        tma_load_2d(dst, tmap, (kc0 + ce) * KC, 0, &rg.full[slot]);
-        tma_load_2d(dst + LO_OFF, tmap, (kc0 + ce) * KC, S, &rg.full[slot]);
+        mbar_arrive_expect_tx(&rg.full[sl], bytes);
+        tma_load_3d(ring_s + sl * SLOT_BYTES, tmap, (kc0 + ce) * KC, 0, half0, &rg.full[sl]);
       }
-      __syncwarp();
-      if (++slot == (uint32_t)nslot) {
-        slot = 0;
-        ++use;
-      }
+      stamp(203);
     }
-  } else if (warp == 9) {
+    __syncwarp();
+  } else if (warp == kIssuerWarp) {
     // ------------------------------ MMA issuer -----------------------------------------------
     const uint32_t ring_s = smem_u32(rg.ring);
     for (int c = 0; c < nch; ++c) {
       mbar_wait(&rg.full[slot], use & 1);
+      if (c == 0) stamp(210);
       tc::tc_fence_after();
       {
         // the whole warp runs the burst on warp-uniform operands; elect.sync predicates the instructions (lstmp_tc.cuh)
@@ -175,10 +220,12 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, const CUte
         ++use;
       }
     }
+    stamp(211);
     tc::tc_fence_before();
-  } else if (warp < 4) {
+  } else if (warp * 32 < 2 * Sg) {
     // ---------------------------- accumulator -> shared memory -------------------------------
     mbar_wait(rg.accum, ps.acc & 1);
+    stamp(50);
     tc::tc_fence_after();
     const int row = warp * 32 + lane;  // TMEM lane = stacked activation row
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
@@ -192,6 +239,7 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, const CUte
         if (c + q < nvalid) rr[c + q] = a[q] + b[q];
     }
     tc::tc_fence_before();
+    stamp(51);
   }
   __syncthreads();
   tc::tc_fence_after();
@@ -199,11 +247,11 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, const CUte
   ps.acc += 1;
 }
 
-__device__ __forceinline__ void store_hl(__nv_bfloat16* base, int S, size_t ld, int s, int col, float v) {
+__device__ __forceinline__ void store_hl(__nv_bfloat16* base, int Sg, size_t ld, int s, int col, float v) {
   __nv_bfloat16 h, l;
   split_bf16(v, h, l);
   base[(size_t)s * ld + col] = h;
-  base[(size_t)(S + s) * ld + col] = l;
+  base[(size_t)(Sg + s) * ld + col] = l;
 }
 }  // namespace tm
 
@@ -218,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
   uint8_t* bg = base + p.off_bg;      // gate weight slice: nch_g tiles of [roundup8(8*cpc) rows][128 B] (hi rows, then lo)
   uint8_t* bp = base + p.off_bp;      // projection slice:  nch_p tiles of [roundup8(2*rpc) rows][128 B]
   float* red = reinterpret_cast<float*>(base + p.off_red);      // [128][ldred]
-  float* cprev = reinterpret_cast<float*>(base + p.off_cprev);  // [S*nc]
+  float* cprev = reinterpret_cast<float*>(base + p.off_cprev);  // [Sg*nc]
   float* peep = reinterpret_cast<float*>(base + p.off_peep);    // [3][cpc]
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + p.off_bars);
   Ring rg;
@@ -226,17 +274,22 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
   rg.full = bars;
   rg.empty = bars + MAX_SLOTS;
   rg.accum = bars + 2 * MAX_SLOTS;
+  rg.gridok = bars + 2 * MAX_SLOTS + 1;
   rg.nslot = p.nslot;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int j = blockIdx.x;
-  const int C = p.C, R = p.R, S = p.S, T = p.T;
+  const int grp = blockIdx.x / p.cpg, j = blockIdx.x - grp * p.cpg;  // stream group, CTA inside the group
+  const int C = p.C, R = p.R, S = p.S, Sg = p.Sg, T = p.T;
+  const int s_base = grp * Sg;
   const int cpc = p.cpc, rpc = p.rpc;
   const int c0 = j * cpc;
   const int nc = max(0, min(cpc, C - c0));  // my cells
   const int r0 = j * rpc;
   const int nr = max(0, min(rpc, R - r0));  // my projection outputs
+  const int row_hi = grp * 2 * Sg;          // first row of my group's hi block in the [G][2][Sg][K] exchange arrays
+  __nv_bfloat16* rhl = p.rhl + (size_t)row_hi * R;
+  __nv_bfloat16* mhl = p.mhl + (size_t)row_hi * C;
 
   if (tid == 0) {
     for (int s = 0; s < p.nslot; ++s) {
@@ -244,9 +297,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
       mbar_init(&rg.empty[s], 1);
     }
     mbar_init(rg.accum, 1);
+    mbar_init(rg.gridok, 1);
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -283,17 +337,17 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
   }
 
   // ---- history: c_0 of my cells -> smem and cbuf block 0; r_0 of my columns -> rbuf block 0 + hi/lo (LPS.h:231) ----
-  for (int idx = tid; idx < S * nc; idx += kThreads) {
+  for (int idx = tid; idx < Sg * nc; idx += kThreads) {
     int s = idx / nc, cl = idx - s * nc;
-    float v = p.state_c[(size_t)s * C + c0 + cl];
+    float v = p.state_c[(size_t)(s_base + s) * C + c0 + cl];
     cprev[idx] = v;
-    p.cbuf[(size_t)s * C + c0 + cl] = v;
+    p.cbuf[(size_t)(s_base + s) * C + c0 + cl] = v;
   }
-  for (int idx = tid; idx < S * nr; idx += kThreads) {
+  for (int idx = tid; idx < Sg * nr; idx += kThreads) {
     int s = idx / nr, n = idx - s * nr;
-    float v = p.state_r[(size_t)s * R + r0 + n];
-    p.rbuf[(size_t)s * R + r0 + n] = v;
-    store_hl(p.rhl, S, (size_t)R, s, r0 + n, v);
+    float v = p.state_r[(size_t)(s_base + s) * R + r0 + n];
+    p.rbuf[(size_t)(s_base + s) * R + r0 + n] = v;
+    store_hl(rhl, Sg, (size_t)R, s, r0 + n, v);
   }
   for (int cl = tid; cl < nc; cl += kThreads) {
     peep[cl] = p.p_i[c0 + cl];
@@ -309,13 +363,16 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
   const uint32_t idesc_g = idesc_bf16(128, p.n_g), idesc_p = idesc_bf16(128, p.n_p);
   const uint32_t bg_s = smem_u32(bg), bp_s = smem_u32(bp);
   const int ldred = (int)p.ldred;
-  const int rot_g = p.stagger ? (int)(blockIdx.x % (unsigned)p.nch_g) : 0;
-  const int rot_p = p.stagger ? (int)(blockIdx.x % (unsigned)p.nch_p) : 0;
+  const int rot_g = p.stagger ? (int)((unsigned)j % (unsigned)p.nch_g) : 0;
+  const int rot_p = p.stagger ? (int)((unsigned)j % (unsigned)p.nch_p) : 0;
 
-  GroupBarrier gb;
-  gb.init(p.bar, p.bar_base, (unsigned)p.nctas, (p.dbg & 1) != 0);
+  GridSync gs;
+  gs.counter = p.bar + grp * 64;
+  gs.target = p.bar_base;
+  gs.nctas = (unsigned)p.cpg;
+  gs.off = (p.dbg & 1) != 0;
   stamp_begin((p.dbg & 4) && blockIdx.x == 0);
-  gb.sync();  // r_0 hi/lo of every CTA is in place
+  if (is_sync_thread()) gs.arrive();  // r_0 hi/lo of this CTA is in place
   stamp(1);
   Pipe ps{0u, 0u};
 
@@ -325,21 +382,22 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
     if (nc > 0) {
       // this thread's first element's x-part pre-activations (input GEMM + bias): in flight during the product
       float xg = 0.f, xi = 0.f, xf = 0.f, xo = 0.f;
-      if (tid < S * nc) {
+      if (tid < Sg * nc) {
         int s = tid / nc, cl = tid - s * nc;
-        const float* gp = p.gifo + (size_t)(tt * S + s) * (4 * C) + c0 + cl;
+        const float* gp = p.gifo + (size_t)(tt * S + s_base + s) * (4 * C) + c0 + cl;
         xg = gp[0];
         xi = gp[C];
         xf = gp[2 * C];
         xo = gp[3 * C];
       }
       // gifo(t) += r(t-1) * W_gifo_r^T                                       (LPS.h:275)
-      tma_product(ps, rg, &p.tm_r, S, 0, p.nch_g, rot_g, bg_s, p.chunk_g, idesc_g, tmem_base + COL_A, 4 * cpc, 4 * nc,
-                  red, ldred);
+      tma_product(ps, rg, gs, true, &p.tm_r, Sg, 2 * grp, 0, p.nch_g, rot_g, bg_s, p.chunk_g, idesc_g, tmem_base + COL_A,
+                  4 * cpc, 4 * nc, red, ldred);
       stamp(11);
-      for (int idx = tid; idx < S * nc; idx += kThreads) {
+      // pass 1: the cell update; only m(t) hi/lo -- what the other CTAs wait for -- is stored before the arrive
+      for (int idx = tid; idx < Sg * nc; idx += kThreads) {
         int s = idx / nc, cl = idx - s * nc;
-        size_t row = (size_t)tt * S + s;
+        size_t row = (size_t)tt * S + s_base + s;
         float* gp = p.gifo + row * (4 * C) + c0 + cl;
         if (idx >= kThreads) {
           xg = gp[0];
@@ -347,8 +405,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
           xf = gp[2 * C];
           xo = gp[3 * C];
         }
-        const float* rh = red + s * ldred + cl;         // hi-activation rows
-        const float* rl = red + (64 + s) * ldred + cl;  // lo-activation rows
+        float* rh = red + s * ldred + cl;         // hi-activation rows
+        float* rl = red + (Sg + s) * ldred + cl;  // lo-activation rows
         float cp = cprev[idx];
         float pi = peep[cl], pf = peep[cpc + cl], po = peep[2 * cpc + cl];
         float ai = (rh[nc] + rl[nc]) + xi + cp * pi;          // :278  i += c(t-1) .* peephole_i_c
@@ -362,50 +420,77 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
         float ao = (rh[3 * nc] + rl[3 * nc]) + xo + c * po;   // :303  (uses c(t), post-clip)
         float go = sigmoidf_fast(ao);                         // :306
         float m = h * go;                                     // :309
-        gp[0] = gg;
-        gp[C] = gi;
-        gp[2 * C] = gf;
-        gp[3 * C] = go;
-        p.cbuf[(row + S) * C + c0 + cl] = c;
-        p.hbuf[row * C + c0 + cl] = h;
-        p.mbuf[row * C + c0 + cl] = m;
-        store_hl(p.mhl, S, (size_t)C, s, c0 + cl, m);
+        store_hl(mhl, Sg, (size_t)C, s, c0 + cl, m);
         cprev[idx] = c;
+        // the record goes to HBM after the arrive (pass 2); park it in the consumed accumulator block meanwhile
+        rh[0] = gg; rh[nc] = gi; rh[2 * nc] = gf; rh[3 * nc] = go;
+        rl[0] = h; rl[nc] = m;
       }
       fence_async_global();
+    } else {
+      if (is_sync_thread()) gs.wait();  // no product: still wait for barrier k before arriving at k+1
     }
+    __syncthreads();
+    if (is_sync_thread()) gs.arrive();
     stamp(20);
-    gb.sync();
-    stamp(21);
+    if (nc > 0) {
+      // pass 2: the activation record (read by the backward launch), off the critical path
+      for (int idx = tid; idx < Sg * nc; idx += kThreads) {
+        int s = idx / nc, cl = idx - s * nc;
+        size_t row = (size_t)tt * S + s_base + s;
+        float* gp = p.gifo + row * (4 * C) + c0 + cl;
+        const float* rh = red + s * ldred + cl;
+        const float* rl = red + (Sg + s) * ldred + cl;
+        gp[0] = rh[0];
+        gp[C] = rh[nc];
+        gp[2 * C] = rh[2 * nc];
+        gp[3 * C] = rh[3 * nc];
+        p.cbuf[(row + S) * C + c0 + cl] = cprev[idx];
+        p.hbuf[row * C + c0 + cl] = rl[0];
+        p.mbuf[row * C + c0 + cl] = rl[nc];
+      }
+      __syncthreads();  // red[] is free for the next product's read-out
+    }
     // ================= phase 2: projection r(t) = m(t) * W_r_m^T for my columns (LPS.h:312) ==
     if (nr > 0) {
-      tma_product(ps, rg, &p.tm_m, S, 0, p.nch_p, rot_p, bp_s, p.chunk_p, idesc_p, tmem_base + COL_B, rpc, nr, red,
-                  ldred);
+      tma_product(ps, rg, gs, true, &p.tm_m, Sg, 2 * grp, 0, p.nch_p, rot_p, bp_s, p.chunk_p, idesc_p, tmem_base + COL_B,
+                  rpc, nr, red, ldred);
       stamp(22);
-      for (int idx = tid; idx < S * nr; idx += kThreads) {
+      for (int idx = tid; idx < Sg * nr; idx += kThreads) {
         int s = idx / nr, n = idx - s * nr;
-        float v = red[s * ldred + n] + red[(64 + s) * ldred + n];
-        size_t row = (size_t)tt * S + s;
-        p.rbuf[(row + S) * R + r0 + n] = v;
-        p.out[row * p.ld_out + r0 + n] = v;                         // :328
-        store_hl(p.rhl, S, (size_t)R, s, r0 + n, v);
-        if (tt == T - 1) p.state_r[(size_t)s * R + r0 + n] = v;     // :331
+        float v = red[s * ldred + n] + red[(Sg + s) * ldred + n];
+        store_hl(rhl, Sg, (size_t)R, s, r0 + n, v);
+        red[s * ldred + n] = v;
       }
       fence_async_global();
+    } else {
+      if (is_sync_thread()) gs.wait();  // no product: still wait for barrier k before arriving at k+1
     }
+    __syncthreads();
+    if (tt + 1 < T && is_sync_thread()) gs.arrive();
     stamp(30);
-    if (tt + 1 < T) gb.sync();
+    if (nr > 0) {
+      for (int idx = tid; idx < Sg * nr; idx += kThreads) {
+        int s = idx / nr, n = idx - s * nr;
+        float v = red[s * ldred + n];
+        size_t row = (size_t)tt * S + s_base + s;
+        p.rbuf[(row + S) * R + r0 + n] = v;
+        p.out[row * p.ld_out + r0 + n] = v;                               // :328
+        if (tt == T - 1) p.state_r[(size_t)(s_base + s) * R + r0 + n] = v;  // :331
+      }
+    }
+    __syncthreads();  // red[] is free for the next product's read-out
     stamp(31);
   }
   // prev_nnet_state_ <- last frame (LPS.h:331): c part
-  for (int idx = tid; idx < S * nc; idx += kThreads) {
+  for (int idx = tid; idx < Sg * nc; idx += kThreads) {
     int s = idx / nc, cl = idx - s * nc;
-    p.state_c[(size_t)s * C + c0 + cl] = cprev[idx];
+    p.state_c[(size_t)(s_base + s) * C + c0 + cl] = cprev[idx];
   }
   stamp_flush(p.dbg_stamps);
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS)
                  : "memory");
@@ -421,11 +506,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
   uint8_t* base = smem_raw_tma + ((1024u - (smem_u32(smem_raw_tma) & 1023u)) & 1023u);
   uint8_t* ba = base + p.off_ba;  // W_gifo_r[my K slice, my cluster's r columns]^T: tiles [roundup8(2*rpb) rows][128 B]
   uint8_t* bb = base + p.off_bb;  // W_r_m[:, my cells]^T: nch_b tiles of [roundup8(2*cpc) rows][128 B]
-  float* red = reinterpret_cast<float*>(base + p.off_red);    // [128][ldred]
-  float* part = reinterpret_cast<float*>(base + p.off_part);  // [S][rpb] my partial d_r block (read by the cluster)
-  float* dgn = reinterpret_cast<float*>(base + p.off_dgn);    // [2][S*cpc]: d_i(t+1), d_f(t+1) of my cells
-  float* dcn = reinterpret_cast<float*>(base + p.off_dcn);    // [S*cpc]    d_c(t+1)
-  float* acc7 = reinterpret_cast<float*>(base + p.off_acc7);  // [S*cpc][7] running sums for bias / peephole gradients
+  float* red = reinterpret_cast<float*>(base + p.off_red);    // [128][ldred]  (phase A: read by the whole cluster)
+  float* dgn = reinterpret_cast<float*>(base + p.off_dgn);    // [2][Sg*cpc]: d_i(t+1), d_f(t+1) of my cells
+  float* dcn = reinterpret_cast<float*>(base + p.off_dcn);    // [Sg*cpc]    d_c(t+1)
+  float* acc7 = reinterpret_cast<float*>(base + p.off_acc7);  // [Sg*cpc][7] running sums for bias / peephole gradients
   float* peep = reinterpret_cast<float*>(base + p.off_peep);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + p.off_bars);
   Ring rg;
@@ -433,19 +517,24 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
   rg.full = bars;
   rg.empty = bars + MAX_SLOTS;
   rg.accum = bars + 2 * MAX_SLOTS;
+  rg.gridok = bars + 2 * MAX_SLOTS + 1;
   rg.nslot = p.nslot;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int j = blockIdx.x;
-  const int C = p.C, R = p.R, S = p.S, T = p.T;
+  const int grp = blockIdx.x / p.cpg, j = blockIdx.x - grp * p.cpg;  // stream group, CTA inside the group
+  const int C = p.C, R = p.R, S = p.S, Sg = p.Sg, T = p.T;
+  const int s_base = grp * Sg;
   const int cpc = p.cpc, rpb = p.rpb, kp = p.kp;
   const int a = (int)cluster_ctarank();  // K slice of the d_r product
-  const int b = j / kp;                  // cluster index: r columns [n0, n0 + nn)
+  const int b = j / kp;                  // cluster index inside the group: r columns [n0, n0 + nn)
   const int n0 = b * rpb;
   const int nn = max(0, min(rpb, R - n0));
   const int c0 = j * cpc;
   const int nc = max(0, min(cpc, C - c0));  // my cells
+  const int row_hi = grp * 2 * Sg;
+  __nv_bfloat16* dghl = p.dghl + (size_t)row_hi * 4 * C;
+  __nv_bfloat16* drhl = p.drhl + (size_t)row_hi * R;
   // my K slice of the 4C contraction, in 64-column chunks
   const int kbase = p.nch_a / kp, krem = p.nch_a % kp;
   const int ks = a * kbase + min(a, krem);
@@ -457,9 +546,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       mbar_init(&rg.empty[s], 1);
     }
     mbar_init(rg.accum, 1);
+    mbar_init(rg.gridok, 1);
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -497,9 +587,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       split8_store(v, t + tc::sw128_off(n, k8 & 7), t + tc::sw128_off(cpc + n, k8 & 7));
     }
   }
-  for (int idx = tid; idx < 2 * S * cpc; idx += kThreads) dgn[idx] = 0.f;  // row-block T+1 is zero (LPS.h:352)
-  for (int idx = tid; idx < S * cpc; idx += kThreads) dcn[idx] = 0.f;
-  for (int idx = tid; idx < S * cpc * 7; idx += kThreads) acc7[idx] = 0.f;
+  for (int idx = tid; idx < 2 * Sg * cpc; idx += kThreads) dgn[idx] = 0.f;  // row-block T+1 is zero (LPS.h:352)
+  for (int idx = tid; idx < Sg * cpc; idx += kThreads) dcn[idx] = 0.f;
+  for (int idx = tid; idx < Sg * cpc * 7; idx += kThreads) acc7[idx] = 0.f;
   for (int cl = tid; cl < nc; cl += kThreads) {
     peep[cl] = p.p_i[c0 + cl];
     peep[cpc + cl] = p.p_f[c0 + cl];
@@ -514,17 +604,20 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
   const uint32_t ba_s = smem_u32(ba), bb_s = smem_u32(bb);
   const int ldred = (int)p.ldred;
   const int rot_a = (p.stagger && nka > 0) ? (int)((unsigned)b % (unsigned)nka) : 0;
-  const int rot_b = p.stagger ? (int)(blockIdx.x % (unsigned)p.nch_b) : 0;
-  const uint32_t part_s = smem_u32(part);
+  const int rot_b = p.stagger ? (int)((unsigned)j % (unsigned)p.nch_b) : 0;
+  const uint32_t red_s = smem_u32(red);
 
-  GroupBarrier gb;
-  gb.init(p.bar, p.bar_base, (unsigned)p.nctas, (p.dbg & 1) != 0);
+  GridSync gs;
+  gs.counter = p.bar + grp * 64;
+  gs.target = p.bar_base;
+  gs.nctas = (unsigned)p.cpg;
+  gs.off = (p.dbg & 1) != 0;
   stamp_begin((p.dbg & 8) && blockIdx.x == 0);
   cluster_sync_all();  // every CTA of the cluster is running (its shared memory may be read from now on)
   stamp(2);
   Pipe ps{0u, 0u};
-  // my share of the cluster's [S x nn] d_r block in the reduction: streams s = a (mod kp)
-  const int nsh = (S - a + kp - 1) / kp;  // streams a, a+kp, ...
+  // my share of the cluster's [Sg x nn] d_r block in the reduction: streams s = a (mod kp)
+  const int nsh = (Sg - a + kp - 1) / kp;  // streams a, a+kp, ...
 
   for (int tt = T - 1; tt >= 0; --tt) {
     const bool have_next = (tt + 1 < T);
@@ -535,18 +628,15 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       float od = 0.f;
       if (tid < nsh * nn) {
         const int s = a + kp * (tid / nn), n = tid % nn;
-        od = p.out_diff[((size_t)tt * S + s) * p.ld_od + n0 + n];
+        od = p.out_diff[((size_t)tt * S + s_base + s) * p.ld_od + n0 + n];
       }
       if (have_next) {
         if (nka > 0) {
-          tma_product(ps, rg, &p.tm_dg, S, ks, nka, rot_a, ba_s, p.chunk_a, idesc_a, tmem_base + COL_A, rpb, nn, red,
-                      ldred);
-          for (int idx = tid; idx < S * nn; idx += kThreads) {
-            const int s = idx / nn, n = idx - s * nn;
-            part[idx] = red[s * ldred + n] + red[(64 + s) * ldred + n];
-          }
+          tma_product(ps, rg, gs, true, &p.tm_dg, Sg, 2 * grp, ks, nka, rot_a, ba_s, p.chunk_a, idesc_a,
+                      tmem_base + COL_A, rpb, nn, red, ldred);
         } else {
-          for (int idx = tid; idx < S * nn; idx += kThreads) part[idx] = 0.f;
+          if (is_sync_thread()) gs.wait();
+          for (int idx = tid; idx < 128 * ldred; idx += kThreads) red[idx] = 0.f;
         }
         stamp(41);
         cluster_sync_all();  // the kp partial blocks of this cluster are complete
@@ -554,27 +644,38 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       }
       for (int li = tid; li < nsh * nn; li += kThreads) {
         const int s = a + kp * (li / nn), n = li % nn;
-        const size_t row = (size_t)tt * S + s;
+        const size_t row = (size_t)tt * S + s_base + s;
         float v = (li < kThreads) ? od : p.out_diff[row * p.ld_od + n0 + n];
         if (have_next) {
-          const uint32_t off = part_s + (uint32_t)((s * nn + n) * 4);
-          for (int q = 0; q < kp; ++q) v += ld_dsmem_f32(off, (uint32_t)q);  // fixed order: bit-reproducible
+          // the kp partial blocks through distributed shared memory, all loads in flight, fixed summation order
+          const uint32_t off_h = red_s + (uint32_t)((s * ldred + n) * 4);
+          const uint32_t off_l = red_s + (uint32_t)(((Sg + s) * ldred + n) * 4);
+          float ph[8], pl[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            ph[q] = q < kp ? ld_dsmem_f32(off_h, (uint32_t)q) : 0.f;
+            pl[q] = q < kp ? ld_dsmem_f32(off_l, (uint32_t)q) : 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v += ph[q] + pl[q];
         }
+        store_hl(drhl, Sg, (size_t)R, s, n0 + n, v);
         p.dr[row * R + n0 + n] = v;
-        store_hl(p.drhl, S, (size_t)R, s, n0 + n, v);
       }
       fence_async_global();
+    } else if (have_next) {
+      if (is_sync_thread()) gs.wait();
     }
+    __syncthreads();
+    if (is_sync_thread()) gs.arrive();
     stamp(43);
-    gb.sync();
-    stamp(44);
     // ============ phase B: d_m = d_r * W_r_m (my cells) (:408) + gate derivatives (:411-440)
     if (nc > 0) {
       // prefetch this thread's first element's activations while d_r is gathered and contracted
       float yg = 0.f, yi = 0.f, yf = 0.f, yo = 0.f, yc = 0.f, ycp = 0.f, yh = 0.f, yfn = 0.f;
-      if (tid < S * nc) {
+      if (tid < Sg * nc) {
         int s = tid / nc, cl = tid - s * nc;
-        size_t row = (size_t)tt * S + s;
+        size_t row = (size_t)tt * S + s_base + s;
         const float* gp = p.gifo + row * (4 * C) + c0 + cl;
         yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
         yc = p.cbuf[(row + S) * C + c0 + cl];
@@ -582,12 +683,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
         yh = p.hbuf[row * C + c0 + cl];
         yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;
       }
-      tma_product(ps, rg, &p.tm_dr, S, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b, tmem_base + COL_B, cpc, nc, red,
-                  ldred);
+      tma_product(ps, rg, gs, true, &p.tm_dr, Sg, 2 * grp, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b,
+                  tmem_base + COL_B, cpc, nc, red, ldred);
       stamp(45);
-      for (int idx = tid; idx < S * nc; idx += kThreads) {
+      for (int idx = tid; idx < Sg * nc; idx += kThreads) {
         int s = idx / nc, cl = idx - s * nc;
-        size_t row = (size_t)tt * S + s;
+        size_t row = (size_t)tt * S + s_base + s;
         if (idx >= kThreads) {
           const float* gp = p.gifo + row * (4 * C) + c0 + cl;
           yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
@@ -597,29 +698,27 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
           yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;  // f(t+1)
         }
         float pi = peep[cl], pf = peep[cpc + cl], po = peep[2 * cpc + cl];
-        float d_m = red[s * ldred + cl] + red[(64 + s) * ldred + cl];
+        float d_m = red[s * ldred + cl] + red[(Sg + s) * ldred + cl];
         float d_h = (d_m * yo) * (1.0f - yh * yh);            // :411-412
         float d_o = (d_m * yh) * yo * (1.0f - yo);            // :415-416
         float d_c = d_h;                                      // :424
         d_c += dcn[idx] * yfn;                                // :425
         d_c += dgn[idx] * pi;                                 // :426
-        d_c += dgn[S * cpc + idx] * pf;                       // :427
+        d_c += dgn[Sg * cpc + idx] * pf;                      // :427
         d_c += d_o * po;                                      // :428
         float d_f = (d_c * ycp) * yf * (1.0f - yf);           // :431-432
         float d_i = (d_c * yg) * yi * (1.0f - yi);            // :435-436
         float d_g = (d_c * yi) * (1.0f - yg * yg);            // :439-440
-        float* dp = p.dgifo + row * (4 * C) + c0 + cl;
-        dp[0] = d_g;
-        dp[C] = d_i;
-        dp[2 * C] = d_f;
-        dp[3 * C] = d_o;
-        store_hl(p.dghl, S, (size_t)4 * C, s, c0 + cl, d_g);
-        store_hl(p.dghl, S, (size_t)4 * C, s, C + c0 + cl, d_i);
-        store_hl(p.dghl, S, (size_t)4 * C, s, 2 * C + c0 + cl, d_f);
-        store_hl(p.dghl, S, (size_t)4 * C, s, 3 * C + c0 + cl, d_o);
+        // DGIFO(t) hi/lo is what the other CTAs wait for; the fp32 record is stored after the arrive
+        store_hl(dghl, Sg, (size_t)4 * C, s, c0 + cl, d_g);
+        store_hl(dghl, Sg, (size_t)4 * C, s, C + c0 + cl, d_i);
+        store_hl(dghl, Sg, (size_t)4 * C, s, 2 * C + c0 + cl, d_f);
+        store_hl(dghl, Sg, (size_t)4 * C, s, 3 * C + c0 + cl, d_o);
         dgn[idx] = d_i;
-        dgn[S * cpc + idx] = d_f;
+        dgn[Sg * cpc + idx] = d_f;
         dcn[idx] = d_c;
+        red[s * ldred + cl] = d_g;         // parked for pass 2 (d_i, d_f are in dgn)
+        red[(Sg + s) * ldred + cl] = d_o;
         float* a7 = acc7 + (size_t)idx * 7;
         a7[0] += d_g;          // bias_corr_ column sums (:474)
         a7[1] += d_i;
@@ -630,24 +729,41 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
         a7[6] += d_o * yc;     // peephole_o_c_corr_  DO(t) .* C(t)    (:483)
       }
       fence_async_global();
+    } else {
+      if (is_sync_thread()) gs.wait();
     }
+    __syncthreads();
+    if (tt > 0 && is_sync_thread()) gs.arrive();
     stamp(46);
-    if (tt > 0) gb.sync();
+    if (nc > 0) {
+      for (int idx = tid; idx < Sg * nc; idx += kThreads) {
+        int s = idx / nc, cl = idx - s * nc;
+        size_t row = (size_t)tt * S + s_base + s;
+        float* dp = p.dgifo + row * (4 * C) + c0 + cl;
+        dp[0] = red[s * ldred + cl];
+        dp[C] = dgn[idx];
+        dp[2 * C] = dgn[Sg * cpc + idx];
+        dp[3 * C] = red[(Sg + s) * ldred + cl];
+      }
+    }
+    __syncthreads();  // red[] is free for the next product's read-out
     stamp(47);
   }
-  // bias / peephole gradients of my cells: sum over the streams in a fixed order, straight into the gradient arena
+  // bias / peephole gradients of my cells: sum over the streams in a fixed order; per-group partials when the streams
+  // are split into groups (summed by small_grads_kernel), else straight into the gradient arena
   // (bias(4C) | peephole_i | peephole_f | peephole_o are contiguous there, LPS.h:162-189)
   __syncthreads();
+  float* gsm = p.g_small + (size_t)grp * 7 * C;
   for (int q = tid; q < nc * 7; q += kThreads) {
     int cl = q / 7, w = q - cl * 7;
     float s7 = 0.f;
-    for (int s = 0; s < S; ++s) s7 += acc7[(size_t)(s * nc + cl) * 7 + w];
-    p.g_small[(size_t)w * C + c0 + cl] = s7;
+    for (int s = 0; s < Sg; ++s) s7 += acc7[(size_t)(s * nc + cl) * 7 + w];
+    gsm[(size_t)w * C + c0 + cl] = s7;
   }
   stamp_flush(p.dbg_stamps);
   tc::tc_fence_before();
   cluster_sync_all();  // nobody exits while a peer may still read its partial block
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS)
                  : "memory");
@@ -659,10 +775,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
 // ------------------------------------------------------------------------------------------------
 static size_t round1k(size_t b) { return (b + 1023) & ~size_t(1023); }
 
-bool fwd_tma_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTmaParams* p, size_t* smem_bytes) {
+bool fwd_tma_plan(int C, int R, int S, int G, int nctas, size_t smem_limit, FwdTmaParams* p, size_t* smem_bytes) {
   using namespace tm;
-  if (S < 1 || S > 64 || (C & 7) || (R & 7) || nctas < 1) return false;
-  const int cpc = (C + nctas - 1) / nctas, rpc = (R + nctas - 1) / nctas;
+  if (G < 1 || S % G || nctas < G) return false;
+  const int Sg = S / G, cpg = nctas / G;
+  if (Sg < 1 || Sg > 64 || (C & 7) || (R & 7)) return false;
+  const int cpc = (C + cpg - 1) / cpg, rpc = (R + cpg - 1) / cpg;
   const int n_g = (8 * cpc + 15) & ~15, n_p = (2 * rpc + 15) & ~15;
   if (n_g > 256 || n_p > 256) return false;
   size_t off = 0;
@@ -671,11 +789,14 @@ bool fwd_tma_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTmaParam
     off += round1k(bytes);
     return (unsigned)o;
   };
+  p->G = G;
+  p->Sg = Sg;
+  p->cpg = cpg;
   p->cpc = cpc;
   p->rpc = rpc;
   p->n_g = n_g;
   p->n_p = n_p;
-  p->nctas = nctas;
+  p->nctas = cpg * G;
   p->nch_g = (R + KC - 1) / KC;
   p->nch_p = (C + KC - 1) / KC;
   p->chunk_g = (unsigned)(((8 * cpc + 7) & ~7) * 128);
@@ -687,7 +808,7 @@ bool fwd_tma_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTmaParam
   p->off_ring = (unsigned)off;
   const int ldred = ((4 * cpc > rpc ? 4 * cpc : rpc) | 1);
   p->ldred = (unsigned)ldred;
-  const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)S * cpc * 4) + 1024 /* peepholes */ +
+  const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)Sg * cpc * 4) + 1024 /* peepholes */ +
                       1024 /* barriers + tmem slot */;
   const size_t reserve = 1024 /* base alignment */ + (size_t)static_smem_reserve();
   if (smem_limit < off + tail + reserve + (size_t)2 * SLOT_BYTES) return false;
@@ -696,18 +817,21 @@ bool fwd_tma_plan(int C, int R, int S, int nctas, size_t smem_limit, FwdTmaParam
   p->nslot = nslot;
   off += (size_t)nslot * SLOT_BYTES;
   p->off_red = take((size_t)128 * ldred * 4);
-  p->off_cprev = take((size_t)S * cpc * 4);
+  p->off_cprev = take((size_t)Sg * cpc * 4);
   p->off_peep = take((size_t)3 * cpc * 4);
   p->off_bars = take(256);
   *smem_bytes = off + 1024;
   return *smem_bytes + (size_t)static_smem_reserve() <= smem_limit;
 }
 
-bool bwd_tma_plan(int C, int R, int S, int nctas, int kp, size_t smem_limit, BwdTmaParams* p, size_t* smem_bytes) {
+// nctas: CTAs of the whole grid (G groups of nctas / G, each a whole number of kp-CTA clusters)
+bool bwd_tma_plan(int C, int R, int S, int G, int nctas, int kp, size_t smem_limit, BwdTmaParams* p, size_t* smem_bytes) {
   using namespace tm;
-  if (S < 1 || S > 64 || (C & 7) || (R & 7) || kp < 1 || kp > 8 || nctas < kp || nctas % kp) return false;
-  const int np = nctas / kp;
-  const int cpc = (C + nctas - 1) / nctas, rpb = (R + np - 1) / np;
+  if (G < 1 || S % G || kp < 1 || kp > 8) return false;
+  const int Sg = S / G, cpg = nctas / G / kp * kp;
+  if (cpg < kp || Sg < 1 || Sg > 64 || (C & 7) || (R & 7)) return false;
+  const int np = cpg / kp;
+  const int cpc = (C + cpg - 1) / cpg, rpb = (R + np - 1) / np;
   const int n_a = (2 * rpb + 15) & ~15, n_b = (2 * cpc + 15) & ~15;
   if (n_a > 256 || n_b > 256) return false;
   size_t off = 0;
@@ -716,7 +840,10 @@ bool bwd_tma_plan(int C, int R, int S, int nctas, int kp, size_t smem_limit, Bwd
     off += round1k(bytes);
     return (unsigned)o;
   };
-  p->nctas = nctas;
+  p->G = G;
+  p->Sg = Sg;
+  p->cpg = cpg;
+  p->nctas = cpg * G;
   p->kp = kp;
   p->cpc = cpc;
   p->rpb = rpb;
@@ -732,8 +859,8 @@ bool bwd_tma_plan(int C, int R, int S, int nctas, int kp, size_t smem_limit, Bwd
   p->off_ring = (unsigned)off;
   const int ldred = ((rpb > cpc ? rpb : cpc) | 1);
   p->ldred = (unsigned)ldred;
-  const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)S * rpb * 4) + round1k((size_t)2 * S * cpc * 4) +
-                      round1k((size_t)S * cpc * 4) + round1k((size_t)S * cpc * 7 * 4) + 1024 + 1024;
+  const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)2 * Sg * cpc * 4) +
+                      round1k((size_t)Sg * cpc * 4) + round1k((size_t)Sg * cpc * 7 * 4) + 1024 + 1024;
   const size_t reserve = 1024 + (size_t)static_smem_reserve();
   if (smem_limit < off + tail + reserve + (size_t)2 * SLOT_BYTES) return false;
   int nslot = (int)((smem_limit - off - tail - reserve) / SLOT_BYTES);
@@ -741,19 +868,18 @@ bool bwd_tma_plan(int C, int R, int S, int nctas, int kp, size_t smem_limit, Bwd
   p->nslot = nslot;
   off += (size_t)nslot * SLOT_BYTES;
   p->off_red = take((size_t)128 * ldred * 4);
-  p->off_part = take((size_t)S * rpb * 4);
-  p->off_dgn = take((size_t)2 * S * cpc * 4);
-  p->off_dcn = take((size_t)S * cpc * 4);
-  p->off_acc7 = take((size_t)S * cpc * 7 * 4);
+  p->off_dgn = take((size_t)2 * Sg * cpc * 4);
+  p->off_dcn = take((size_t)Sg * cpc * 4);
+  p->off_acc7 = take((size_t)Sg * cpc * 7 * 4);
   p->off_peep = take((size_t)3 * cpc * 4);
   p->off_bars = take(256);
   *smem_bytes = off + 1024;
   return *smem_bytes + (size_t)static_smem_reserve() <= smem_limit;
 }
 
-// [2*S rows x K] bf16 row-major array -> tensor map with [S rows x 64 k] boxes, 128-byte swizzle, zero fill outside
-// (the K tail of the last box).  cuTensorMapEncodeTiled is resolved through the runtime (no link against libcuda).
-int make_hl_tensor_map(void* out_map, const void* gptr, int rows, int K, int box_rows) {
+// [group][hi|lo][Sg] x K bf16 array -> 3-D tensor map with [2 halves][Sg rows][64 k] boxes, 128-byte swizzle, zero
+// fill outside (the K tail of the last box).  cuTensorMapEncodeTiled is resolved through the runtime (no link against libcuda).
+int make_hl_tensor_map(void* out_map, const void* gptr, int halves, int Sg, int K) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -765,11 +891,12 @@ int make_hl_tensor_map(void* out_map, const void* gptr, int rows, int K, int box
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) return -1;
     fn = (encode_fn)sym;
   }
-  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)tm::KC, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr),
+  // dims (fastest first): k, stream within the half, half index (2*group + {hi, lo}); box = [2 halves][Sg][64 k]
+  const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)Sg, (cuuint64_t)halves};
+  const cuuint64_t gstride[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * (cuuint64_t)Sg};
+  const cuuint32_t box[3] = {(cuuint32_t)tm::KC, (cuuint32_t)Sg, 2u};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr),
                   gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;

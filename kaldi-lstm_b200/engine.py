@@ -117,6 +117,12 @@ class _CudaArray:
         }
 
 
+def _cur_stream(device):
+    """The current torch stream of `device` (an engine's own device, not whatever device happens to be current)."""
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
 class Engine:
     """One LstmProjectedStreams layer resident on one B200."""
 
@@ -139,10 +145,8 @@ class Engine:
         except Exception:
             pass
 
-    @staticmethod
-    def _stream():
-        import torch
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self):
+        return _cur_stream(self.device)
 
     @property
     def num_params(self):
@@ -233,6 +237,12 @@ class Engine:
     def update(self, learn_rate, momentum):
         _chk(load_library().lstmp_b200_update(self._h, float(learn_rate), float(momentum), self._stream()))
 
+    def allreduce_grads_nccl(self, comm_ptr, stream_ptr=None):
+        """Sum all-reduce of the fresh-gradient arena over the raw ncclComm_t `comm_ptr` on `stream_ptr` (a
+        cudaStream_t as int; default: the current stream)."""
+        st = ctypes.c_void_p(stream_ptr) if stream_ptr is not None else self._stream()
+        _chk(load_library().lstmp_b200_allreduce_grads_nccl(self._h, ctypes.c_void_p(comm_ptr), st))
+
     def timing_enable(self, on=True):
         _chk(load_library().lstmp_b200_timing_enable(self._h, 1 if on else 0))
 
@@ -304,13 +314,13 @@ class XentEngine:
         _chk(load_library().lstmp_b200_xent_eval_masked(
             self._h, ctypes.c_void_p(mask.ctypes.data), po, ldo, rows, num_pdf, ctypes.c_void_p(rp.ctypes.data),
             ctypes.c_void_p(pd.ctypes.data) if pd.size else None, ctypes.c_void_p(wt.ctypes.data) if wt.size else None,
-            pdiff, ldd, Engine._stream()))
+            pdiff, ldd, _cur_stream(self.device)))
 
     def stats(self):
         st = XentStats()
-        _chk(load_library().lstmp_b200_xent_get_stats(self._h, ctypes.byref(st), Engine._stream()))
+        _chk(load_library().lstmp_b200_xent_get_stats(self._h, ctypes.byref(st), _cur_stream(self.device)))
         return {"loss": st.loss, "entropy": st.entropy, "correct": int(st.correct), "frames": int(st.frames),
                 "kernel_launches": int(st.kernel_launches)}
 
     def reset_stats(self):
-        _chk(load_library().lstmp_b200_xent_reset_stats(self._h, Engine._stream()))
+        _chk(load_library().lstmp_b200_xent_reset_stats(self._h, _cur_stream(self.device)))

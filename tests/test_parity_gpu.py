@@ -161,6 +161,17 @@ def test_backward_cluster_sizes(klb, oracle_blas, kp, monkeypatch):
     assert info["bwd_tensor_core"] == 2 and info["bwd_cluster"] == kp and info["bwd_ctas"] % kp == 0
 
 
+@pytest.mark.parametrize("groups", [1, 2])
+def test_tma_stream_groups(klb, oracle_blas, groups, monkeypatch):
+    """One or two independent stream groups (own grid barrier, own rows of the hi/lo exchange arrays)."""
+    from parity_util import run_pair
+    monkeypatch.setenv("LSTMP_B200_TMA_GROUPS", str(groups))
+    _, comp, _ = run_pair(klb, oracle_blas, I=40, C=256, R=128, S=64, T=6, nchunks=2, scale=0.08, seed=80 + groups,
+                          check_record=True, resets=[None, (np.arange(64) % 5 == 0).astype(np.int32)])
+    info = comp.engine.info()
+    assert info["fwd_tensor_core"] == 2 and info["ngroups"] == groups and info["streams_per_group"] == 64 // groups
+
+
 def test_tma_loops_few_ctas(klb, oracle_mod, monkeypatch):
     """Few CTAs with many cells / columns each: multi-round elementwise loops, wide MMA N, one cluster."""
     from parity_util import run_pair
