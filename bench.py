@@ -127,23 +127,36 @@ def alg_chunk(I, C, R, S, T):
 # cblas sgemm + serial elementwise loops) on this box's host cores
 # ---------------------------------------------------------------------------------------------
 class CpuStack:
+    """The CPU arm: oracle/_ref (the reference's own LstmProjectedStreams compiled from /root/reference against a CPU
+    Kaldi surface; kind "reference") when it was built, else the C restatement oracle/lstmp_streams_oracle.c
+    (kind "port").  Same Python interface either way."""
+
     def __init__(self, wl, threads=None):
-        from oracle import oracle_py
-        oracle_py.build()
+        from oracle import oracle_py, ref_py
         if threads is None:
             threads = min(os.cpu_count() or 1, 64)   # scipy's OpenBLAS is built for at most 64 threads
-        self.threads = oracle_py.use_openblas(threads) or 1
-        self.blas = "openblas(scipy-bundled)" if self.threads and oracle_py._blas_keepalive else "builtin-loops"
+        if ref_py.available():
+            self.kind, self.mod, Layer = "reference", ref_py, ref_py.RefLstm
+            self.what = "oracle/_ref: the reference's own bd-nnet-lstm-projected-streams.h on its CPU matrix path"
+        else:
+            oracle_py.build()
+            self.kind, self.mod, Layer = "port", oracle_py, oracle_py.Oracle
+            self.what = "oracle/lstmp_streams_oracle.c (oracle/_ref not built on this machine)"
+        self.threads = self.mod.use_openblas(threads) or 1
+        self.blas = "openblas(scipy-bundled)" if self.threads > 0 and self.mod.use_openblas(threads) else "builtin-loops"
         self.S, self.T = wl["S"], wl["T"]
         self.layers = []
         for li, (I, C, R) in enumerate(wl["layers"]):
-            o = oracle_py.Oracle(I, C, R, self.S, np.float32)
+            o = Layer(I, C, R, self.S, np.float32)
             o.set_params(oracle_py.init_params(I, C, R, PARAM_SCALE, 4321 + li))
             self.layers.append(o)
         rng = np.random.RandomState(1234)
         I0, Rtop = wl["layers"][0][0], wl["layers"][-1][2]
         self.x = rng.randn(self.S * self.T, I0).astype(np.float32)
         self.od = (rng.randn(self.S * self.T, Rtop) * 0.1).astype(np.float32)
+
+    def set_threads(self, n):
+        return self.mod.use_openblas(n) or 0
 
     def step(self):
         acts = [self.x]
@@ -158,6 +171,36 @@ class CpuStack:
     def frames(self):
         return self.S * self.T
 
+    def single_thread_sample(self, seconds=2.0, max_steps=20):
+        """Kaldi's nnet1 default is a single-threaded BLAS: a short 1-thread sample."""
+        try:
+            if not self.set_threads(1):
+                return None
+            t1 = time.perf_counter()
+            n1 = 0
+            while n1 < 1 or (time.perf_counter() - t1 < seconds and n1 < max_steps):
+                self.step()
+                n1 += 1
+            out = {"value": self.frames() * n1 / (time.perf_counter() - t1), "unit": "frames/s", "cores": 1,
+                   "sample": "%d full chunks" % n1}
+            self.set_threads(self.threads)
+            return out
+        except Exception as e:
+            return {"error": str(e)[:200]}
+
+
+def workload_config(args, wl, world):
+    """The `config` object: identical for both arms (the driver compares them)."""
+    I0, Rtop = wl["layers"][0][0], wl["layers"][-1][2]
+    bytes_per_chunk = wl["S"] * wl["T"] * (I0 + Rtop) * 4
+    ring = max(4, int(160e6 // bytes_per_chunk) + 1)
+    return {"workload": wl["desc"], "name": args.workload, "num_stream_per_gpu": wl["S"], "bptt_frames": wl["T"],
+            "learn_rate": LR, "momentum": MOMENTUM, "param_scale": PARAM_SCALE,
+            "parallelism": ("streams sharded over %d GPU(s), 1 NCCL sum-allreduce of each layer's gradients per Update, "
+                            "overlapped with the backward pass of the layer below" % world) if world > 1 else "1 GPU",
+            "l2": "GPU arm: inputs larger than L2, a ring of %d distinct (feature, out_diff) chunks = %.0f MB" % (
+                ring, ring * bytes_per_chunk / 1e6)}
+
 
 def run_reference_arm(args, wl):
     stack = CpuStack(wl)
@@ -168,33 +211,19 @@ def run_reference_arm(args, wl):
         stack.step()
     dt = time.perf_counter() - t0
     val = stack.frames() * args.steps / dt
-    # Kaldi's nnet1 default is a single-threaded BLAS: time a short single-thread sample as well
-    single = None
-    try:
-        from oracle import oracle_py
-        if oracle_py.use_openblas(1):
-            t1 = time.perf_counter()
-            n1 = 0
-            while n1 < 1 or (time.perf_counter() - t1 < 2.0 and n1 < 20):
-                stack.step()
-                n1 += 1
-            single = {"value": stack.frames() * n1 / (time.perf_counter() - t1), "unit": "frames/s", "cores": 1,
-                      "sample": "%d full chunks" % n1}
-    except Exception as e:
-        single = {"error": str(e)[:200]}
+    single = stack.single_thread_sample()
     line = {
         "impl": "reference", "metric": "frames/sec LstmProjectedStreams 800-cell/512-proj BPTT", "value": val,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload, "num_stream": wl["S"], "bptt_frames": wl["T"]},
-        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": stack.threads, "kind": "port",
-                         "sample": "%d full chunks of the workload; sgemm=%s, elementwise loops serial as in "
-                                   "kaldi-matrix.cc" % (args.steps, stack.blas), "single_thread": single},
+        "config": workload_config(args, wl, args.gpus),
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": stack.threads, "kind": stack.kind,
+                         "sample": "%d full chunks of the workload; %s; sgemm=%s on %d threads (host has %d cpus), "
+                                   "elementwise loops serial as in kaldi-matrix.cc" % (
+                                       args.steps, stack.what, stack.blas, stack.threads, os.cpu_count()),
+                         "single_thread": single},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference cannot be compiled here (no Kaldi tree); this is the oracle restatement of its CPU "
-                "matrix path (oracle/lstmp_streams_oracle.c) on %d host threads (host has %d)" % (stack.threads,
-                                                                                                     os.cpu_count()),
     }
     print(json.dumps(line), flush=True)
 
@@ -284,6 +313,60 @@ def bench_xent(args):
     return 0
 
 
+def mgpu_parity_check(klb, exchange, dev, rank, world):
+    """N > 1, before the timed region: (1) N ranks x S/N streams through the engine's own NCCL entry point
+    (lstmp_b200_allreduce_grads_nccl) reproduce ONE engine running all S streams on this rank's GPU; (2) the replicas stay
+    bit-identical across ranks.  Small shape, 3 chunks with state carry-over, momentum 0.9.  Returns a dict for the JSON
+    line; never raises (a failure is reported, not hidden)."""
+    import torch
+    import torch.distributed as dist
+    try:
+        I, C, R, T, nchunks = 40, 256, 128, 6, 3
+        Sl = 16
+        Stot = Sl * world
+        full = klb.LstmProjectedStreams(I, R, device=dev.index, max_frames=T)
+        full.InitData("<CellDim> %d <NumStream> %d <ParamScale> 0.1" % (C, Stot), seed=99)
+        full.SetTrainOptions(klb.NnetTrainOptions(1e-3, 0.9))
+        part = klb.LstmProjectedStreams(I, R, device=dev.index, max_frames=T)
+        part.InitData("<CellDim> %d <NumStream> %d" % (C, Sl))
+        part.SetParams(full.GetParams())
+        part.SetTrainOptions(klb.NnetTrainOptions(1e-3, 0.9))
+        ex = klb.parallel.GradientExchange([part], dev)
+        g = torch.Generator(device=dev).manual_seed(4242)      # same data on every rank
+        worst = 0.0
+        for n in range(nchunks):
+            x = torch.randn(T, Stot, I, device=dev, generator=g)
+            od = torch.randn(T, Stot, R, device=dev, generator=g) * 0.1
+            of = full.Propagate(x.reshape(T * Stot, I))
+            full.Backpropagate(x.reshape(T * Stot, I), of, od.reshape(T * Stot, R), want_in_diff=False)
+            full.Update()
+            xs = x[:, rank * Sl:(rank + 1) * Sl].reshape(T * Sl, I).contiguous()
+            ods = od[:, rank * Sl:(rank + 1) * Sl].reshape(T * Sl, R).contiguous()
+            op = part.Propagate(xs)
+            part.Backpropagate(xs, op, ods, want_in_diff=False)
+            ex.start(0)
+            ex.finish(0)
+            part.Update()
+            ref_out = of.reshape(T, Stot, R)[:, rank * Sl:(rank + 1) * Sl].reshape(T * Sl, R)
+            worst = max(worst, float((op - ref_out).abs().max() / ref_out.abs().max()))
+        pf = torch.from_numpy(full.GetParams()).to(dev)
+        pp = torch.from_numpy(part.GetParams()).to(dev)
+        err = float((pp - pf).abs().max() / pf.abs().max())
+        lo, hi = pp.clone(), pp.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        identical = bool(torch.equal(lo, hi))
+        t = torch.tensor([err, worst], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ex.close()
+        return {"ok": bool(identical and float(t[0]) <= 1e-4 and float(t[1]) <= 1e-4), "replicas_bit_identical": identical,
+                "params_vs_single_engine_rel": float(t[0]), "out_vs_single_engine_rel": float(t[1]),
+                "shape": "%d ranks x %d streams vs 1 x %d streams, 40->256/128, T=%d, %d chunks" % (world, Sl, Stot, T, nchunks),
+                "allreduce": "lstmp_b200_allreduce_grads_nccl on an own ncclComm_t, side stream"}
+    except Exception as e:  # report, do not hide
+        return {"ok": False, "error": str(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,9 +425,11 @@ def main():
     outs = [torch.empty(rows, R, device=dev) for (_, _, R) in wl["layers"]]
     in_diffs = [None] + [torch.empty(rows, I, device=dev) for (I, _, _) in wl["layers"][1:]]
 
-    def compute(x, od, i):
-        # staggered synthetic utterance boundaries: stream s starts a new utterance every 50 chunks
-        flags = [1 if (i + s) % 50 == 0 else 0 for s in range(S)]
+    exchange = klb.parallel.GradientExchange(layers, dev) if world > 1 else None
+
+    def compute(x, od, i, flags=None):
+        if flags is None:   # staggered synthetic utterance boundaries: stream s starts a new utterance every 50 chunks
+            flags = [1 if (i + s) % 50 == 0 else 0 for s in range(S)]
         h = x
         for li, comp in enumerate(layers):
             comp.Reset(flags)                                 # nnet.Reset(new_utt_flags), TRAIN.cc:209
@@ -355,10 +440,11 @@ def main():
             inp = x if li == 0 else outs[li - 1]
             layers[li].BackpropagateFnc(inp, outs[li], d, in_diffs[li])
             d = in_diffs[li]
-        if world > 1:                                         # one sum all-reduce of the fresh gradients per Update
-            for gv in grad_views:
-                dist.all_reduce(gv, op=dist.ReduceOp.SUM)     # == klb.parallel.allreduce_gradients(layers)
-        for comp in layers:
+            if exchange is not None:                          # layer li's gradient is final: all-reduce it on the side
+                exchange.start(li)                            # stream while the layers below run their backward
+        for li, comp in enumerate(layers):
+            if exchange is not None:
+                exchange.finish(li)                           # Update(li) waits for its own all-reduce only
             comp.Update()
 
     def launches():
@@ -369,6 +455,8 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    mgpu_parity = mgpu_parity_check(klb, exchange, dev, rank, world) if world > 1 else None
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -394,42 +482,87 @@ def main():
         ms = float(t.item())
     value = world * rows * args.steps / (ms * 1e-3)
 
-    # ---- end-to-end: host buffers in, host scalar out, through the same public calls --------------
+    # ---- end-to-end: host utterances in, host scalar out, through the same public calls --------------
+    # The trainer's loop (TRAIN.cc:143-229): utterances live in HOST memory; the stream dispatcher uploads each one
+    # once when a stream takes it (pinned staging, own copy stream) and assembles the time-major chunk on the device
+    # with the delay shift, padding and the CMVN transform; the loss-gradient stand-in goes H2D from pinned memory on a
+    # copy stream (double-buffered); every step's result (4-byte checksum of the top output) comes back D2H and is
+    # read by the host one step later (the next step's uploads are already in flight then).
     e2e = None
     if not args.no_e2e:
-        nh = min(ring, 16)
-        Xh = [torch.randn(rows, I0).pin_memory() for _ in range(nh)]
+        rng = np.random.RandomState(777 + rank)
+        pool = [("u%d" % k, rng.randn(int(rng.randint(300, 701)), I0).astype(np.float32)) for k in range(192)]
+        pool = [(k, f, rng.randint(0, 8000, size=f.shape[0])) for k, f in pool]
+
+        def utterances():
+            k = 0
+            while True:
+                yield pool[k % len(pool)]
+                k += 1
+        shift = (rng.randn(I0) * 3).astype(np.float32)
+        scale = (0.25 + 0.001 * np.arange(I0)).astype(np.float32)
+        disp = klb.DeviceStreamDispatcher(S, T, 5, I0, max_utt_frames=704, device=local_rank, shift=shift, scale=scale)
+        disp.open(utterances())
+        nh = 8
         ODh = [(torch.randn(rows, Rtop) * 0.1).pin_memory() for _ in range(nh)]
-        xd, odd = torch.empty(rows, I0, device=dev), torch.empty(rows, Rtop, device=dev)
-        res = torch.empty(1).pin_memory()
+        xd = [torch.empty(rows, I0, device=dev) for _ in range(2)]
+        odd = [torch.empty(rows, Rtop, device=dev) for _ in range(2)]
+        res = [torch.empty(1).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        od_ready = [torch.cuda.Event() for _ in range(2)]
+        od_free = [torch.cuda.Event() for _ in range(2)]
+        res_ready = [torch.cuda.Event() for _ in range(2)]
+        main_stream = torch.cuda.current_stream(dev)
 
-        def e2e_step(i):
-            xd.copy_(Xh[i % nh], non_blocking=True)          # feature chunk H2D (TRAIN.cc:212 CuMatrix(feat))
-            odd.copy_(ODh[i % nh], non_blocking=True)        # loss gradient stand-in (targets go H2D in LOSS.cc:96)
-            compute(xd, odd, i)
-            res.copy_(outs[-1][rows - S:].sum().reshape(1), non_blocking=False)   # progress metric D2H + sync
-            return float(res[0])
+        def e2e_enqueue(i):
+            b = i & 1
+            feat, mask, target, flags = disp.next_chunk(feat_out=xd[b])   # utterance uploads + gather kernel
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(od_free[b])
+                odd[b].copy_(ODh[i % nh], non_blocking=True)     # loss gradient stand-in (targets go H2D in LOSS.cc:96)
+                od_ready[b].record(copy_stream)
+            main_stream.wait_event(od_ready[b])
+            compute(xd[b], odd[b], i, flags=flags.tolist())
+            od_free[b].record(main_stream)
+            res[b].copy_(outs[-1][rows - S:].sum().reshape(1), non_blocking=True)   # progress metric D2H
+            res_ready[b].record(main_stream)
 
-        for i in range(3):
-            e2e_step(i)
+        def e2e_collect(i):
+            res_ready[i & 1].synchronize()
+            return float(res[i & 1][0])
+
+        for i in range(4):
+            e2e_enqueue(i)
+            if i:
+                e2e_collect(i - 1)
+        e2e_collect(3)
         sync_all()
+        st0 = disp.stats()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for i in range(args.steps):
-            e2e_step(i)
+            e2e_enqueue(4 + i)
+            if i:
+                e2e_collect(4 + i - 1)
+        e2e_collect(4 + args.steps - 1)
         s1.record()
         sync_all()
+        st1 = disp.stats()
         ems = s0.elapsed_time(s1)
         if world > 1:
             t = torch.tensor([ems], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         e2e = {"value": world * rows * args.steps / (ems * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": rows * (I0 + Rtop) * 4, "d2h_bytes_per_step": 4,
-               "ms_per_step": ems / args.steps,
-               "what": "pinned host feature chunk + loss-gradient chunk H2D, Reset/Propagate/Backpropagate/"
-                       "[allreduce]/Update through the component API, 4-byte output checksum D2H with sync, "
-                       "every step"}
+               "h2d_bytes_per_step": int((st1["h2d_bytes"] - st0["h2d_bytes"]) / args.steps + rows * Rtop * 4),
+               "d2h_bytes_per_step": 4, "ms_per_step": ems / args.steps,
+               "utterances_uploaded": st1["utterances_loaded"] - st0["utterances_loaded"],
+               "what": "host utterances -> DeviceStreamDispatcher (each utterance H2D once from pinned staging on its own "
+                       "copy stream; delay shift, padding and CMVN in one gather kernel) + pinned loss-gradient chunk H2D "
+                       "on a copy stream, Reset/Propagate/Backpropagate/[allreduce]/Update through the component API, "
+                       "4-byte output checksum D2H every step, read by the host one step later"}
+        disp.close()
 
     # ---- per-kernel device times (engine-side CUDA events on the launch stream) -------------------
     for c in layers:
@@ -467,9 +600,10 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
-    fwd_tc = bool(layers[0].engine.info().get("fwd_tensor_core"))
-    roofline = {"kernel": ("lstmp_fwd_tc_kernel" if fwd_tc else "lstmp_fwd_kernel") if dom == "fwd_recurrent"
-                else "lstmp_bwd_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+    inf0 = layers[0].engine.info()
+    fwd_name = {2: "lstmp_fwd_tma_kernel", 1: "lstmp_fwd_tc_kernel"}.get(inf0.get("fwd_tensor_core"), "lstmp_fwd_kernel")
+    bwd_name = "lstmp_bwd_tma_kernel" if inf0.get("bwd_tensor_core") == 2 else "lstmp_bwd_kernel"
+    roofline = {"kernel": fwd_name if dom == "fwd_recurrent" else bwd_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                 "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None, "traffic": traffic,
                 "peak_source": peak_src, "alg_bytes_per_launch": ab, "alg_flops_per_launch": af,
                 "us_per_launch": dom_us, "achieved_tflops_fp32": af / (dom_us * 1e-6) / 1e12 if ach else None}
@@ -494,10 +628,11 @@ def main():
             stack.step()
             n += 1
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": stack.frames() * n / dt, "unit": "frames/s", "cores": stack.threads, "kind": "port",
-                        "sample": "%d full chunks (%.1f s) of the same workload; sgemm=%s on %d threads (host has %d "
-                                  "cpus), elementwise loops serial as in kaldi-matrix.cc" % (
-                                      n, dt, stack.blas, stack.threads, os.cpu_count())}
+        cpu_baseline = {"value": stack.frames() * n / dt, "unit": "frames/s", "cores": stack.threads, "kind": stack.kind,
+                        "sample": "%d full chunks (%.1f s) of the same workload; %s; sgemm=%s on %d threads (host has "
+                                  "%d cpus), elementwise loops serial as in kaldi-matrix.cc" % (
+                                      n, dt, stack.what, stack.blas, stack.threads, os.cpu_count()),
+                        "single_thread": stack.single_thread_sample()}
 
     secondary = None
     if rank == 0 and world == 1 and args.workload == "cfg3" and not args.no_secondary:
@@ -556,23 +691,80 @@ def main():
         except Exception as e:
             secondary["forward_only"] = {"error": str(e)[:200]}
 
+    # ---- N > 1: the other configurations BASELINE.json names for 8 GPUs, device-resident, same timing rules --------
+    if world > 1 and not args.no_secondary:
+        def measure_stack(shapes, S2, T2, nsteps):
+            ls = []
+            for li, (I, C, R) in enumerate(shapes):
+                c = klb.LstmProjectedStreams(I, R, device=local_rank, max_frames=T2)
+                c.InitData("<CellDim> %d <NumStream> %d <ParamScale> %g" % (C, S2, PARAM_SCALE), seed=4321 + li)
+                c.SetTrainOptions(klb.NnetTrainOptions(LR, MOMENTUM))
+                ls.append(c)
+            ex = klb.parallel.GradientExchange(ls, dev)
+            r2 = S2 * T2
+            nr = 8
+            xs = torch.randn(nr, r2, shapes[0][0], device=dev)
+            ods = torch.randn(nr, r2, shapes[-1][2], device=dev) * 0.1
+            o2 = [torch.empty(r2, R, device=dev) for (_, _, R) in shapes]
+            idf = [None] + [torch.empty(r2, I, device=dev) for (I, _, _) in shapes[1:]]
+
+            def step(i):
+                h = xs[i % nr]
+                for li, c in enumerate(ls):
+                    c.PropagateFnc(h, o2[li])
+                    h = o2[li]
+                d = ods[i % nr]
+                for li in reversed(range(len(ls))):
+                    ls[li].BackpropagateFnc(xs[i % nr] if li == 0 else o2[li - 1], o2[li], d, idf[li])
+                    d = idf[li]
+                    ex.start(li)
+                for li, c in enumerate(ls):
+                    ex.finish(li)
+                    c.Update()
+            for i in range(3):
+                step(i)
+            sync_all()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(nsteps):
+                step(i)
+            a1.record()
+            sync_all()
+            t = torch.tensor([a0.elapsed_time(a1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ex.close()
+            m = float(t.item())
+            return {"value": world * r2 * nsteps / (m * 1e-3), "unit": "frames/s", "ms_per_step": m / nsteps,
+                    "steps": nsteps, "num_stream_per_gpu": S2, "num_stream_total": S2 * world}
+        secondary = {}
+        try:
+            if 256 % world == 0:
+                r = measure_stack([(40, 800, 512)], 256 // world, 20, 50)
+                r["workload"] = ("configs[3] LSTM part, STRONG scaling: 40->800/512, NumStream=256 in total = %d per GPU, "
+                                 "T=20" % (256 // world))
+                secondary["cfg4_lstm_strong"] = r
+        except Exception as e:
+            secondary["cfg4_lstm_strong"] = {"error": str(e)[:200]}
+        try:
+            r = measure_stack([(40, 2048, 1024)], 64, 20, 10)
+            r["workload"] = "configs[4]: 40->2048/1024, NumStream=64 per GPU (weak), T=20 (weights-streamed mode)"
+            secondary["cfg5"] = r
+        except Exception as e:
+            secondary["cfg5"] = {"error": str(e)[:200]}
+
     if rank == 0:
         info = layers[0].engine.info()
         line = {
             "metric": "frames/sec LstmProjectedStreams 800-cell/512-proj BPTT", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "num_stream_per_gpu": S, "bptt_frames": T,
-                       "learn_rate": LR, "momentum": MOMENTUM, "param_scale": PARAM_SCALE,
-                       "parallelism": "streams sharded over %d GPU(s), 1 NCCL sum-allreduce of the gradients per "
-                                      "Update" % world if world > 1 else "1 GPU",
-                       "l2": "inputs larger than L2: ring of %d distinct (feature, out_diff) chunks = %.0f MB" % (
-                           ring, ring * bytes_per_chunk / 1e6),
-                       "decomposition": {k: info[k] for k in ("fwd_tensor_core", "ngroups", "ctas_per_group", "streams_per_group",
-                                                              "cells_per_cta", "rcols_per_cta", "gemm_backend")}},
+            "config": workload_config(args, wl, world),
+            "engine": {k: info[k] for k in ("fwd_tensor_core", "bwd_tensor_core", "ngroups", "ctas_per_group",
+                                            "streams_per_group", "cells_per_cta", "rcols_per_cta", "bwd_ctas",
+                                            "bwd_cluster", "gemm_backend")},
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": sampler.summary(), "roofline": roofline,
             "chunk_roofline": chunk_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
-            "secondary": secondary,
+            "secondary": secondary, "mgpu_parity": mgpu_parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -167,6 +167,44 @@ int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, int N, int K
                           size_t lda, int tA, const float* B, size_t ldb, int tB, float beta, const float* bias,
                           void* stream);
 
+/* Update with the element-wise gradient clipping of the single-stream `standard/` component
+ * (standard/nnet/nnet-lstm-projected.h:469-493): corr = G + momentum*corr (the AddMatMat beta of :438-460); every
+ * element of corr clamped to [-max_grad, +max_grad] IN PLACE (ClipGradMat / ClipGradVec, :469-478, max_grad = 50 at
+ * :482); param -= learn_rate * corr.  max_grad <= 0 means no clipping (== lstmp_b200_update). */
+int lstmp_b200_update_clipped(lstmp_b200_handle_t h, float learn_rate, float momentum, float max_grad, void* stream);
+
+/* ---- Multi-stream chunk assembly on the device -------------------------------------
+ * Replaces the host-side batch fill of the trainer (google/nnetbin/bd-nnet-train-lstm-streams.cc:187-206, feature
+ * part), the per-chunk H2D copy of the [T*S x D] chunk (:212) and the AddShift + Rescale feature transform
+ * (google/feature_transform.nnet.txt:2-5).  An utterance goes host -> device ONCE, when a stream takes it
+ * (load_utt, TRAIN.cc:152-170: pinned staging + async copy on the dispatcher's own stream, two device slots per
+ * stream); per chunk `assemble` copies 3*S ints and runs one gather kernel:
+ *   feat[t*S + s] = transform(utt_s[min(curt[s] + t + targets_delay, lent[s] - 1)])   (zeros when lent[s] == 0)
+ * with transform(x) = (x + shift) * scale, bit-identical to the host loop.  curt / lent / targets / frame_mask /
+ * new_utt_flags stay with the caller (kaldi/b200-stream-dispatch.h mirrors the reference loop).  feat_dim % 4 == 0. */
+typedef struct lstmp_b200_dispatch* lstmp_b200_dispatch_handle_t;
+int lstmp_b200_dispatch_create(int num_stream, int batch_size, int targets_delay, int feat_dim, int max_utt_frames,
+                               int device, lstmp_b200_dispatch_handle_t* out);
+int lstmp_b200_dispatch_destroy(lstmp_b200_dispatch_handle_t h);
+/* shift / scale: HOST vectors of feat_dim floats, either may be NULL (component absent). */
+int lstmp_b200_dispatch_set_transform(lstmp_b200_dispatch_handle_t h, const float* shift, const float* scale);
+/* feats: HOST matrix [num_frames x feat_dim], row stride ld; the copy is asynchronous, feats may be freed on return. */
+int lstmp_b200_dispatch_load_utt(lstmp_b200_dispatch_handle_t h, int stream, const float* feats, size_t ld,
+                                 int num_frames);
+/* curt, lent: HOST int32[num_stream] as BEFORE this chunk's fill (the caller advances curt by batch_size afterwards,
+ * TRAIN.cc:204); feat: DEVICE [batch_size*num_stream x feat_dim], row stride ld_feat (a multiple of 4). */
+int lstmp_b200_dispatch_assemble(lstmp_b200_dispatch_handle_t h, const int32_t* curt, const int32_t* lent, float* feat,
+                                 size_t ld_feat, void* stream);
+typedef struct {
+  unsigned long long kernel_launches, h2d_bytes, utterances_loaded, chunks_assembled;
+} lstmp_b200_dispatch_stats_t;
+int lstmp_b200_dispatch_get_stats(lstmp_b200_dispatch_handle_t h, lstmp_b200_dispatch_stats_t* out);
+
+/* TimeShift::PropagateFnc (standard/nnet/nnet-time-shift.h:42-51): out row dst = in row clamp(dst + shift, 0,
+ * num_rows - 1); device matrices, out must not alias in.  (Its BackpropagateFnc is empty in the reference, :53-56.) */
+int lstmp_b200_time_shift(const float* in, size_t ld_in, float* out, size_t ld_out, int num_rows, int num_cols, int shift,
+                          void* stream);
+
 /* ---- Masked cross-entropy with sparse targets --------------------------------
  * Replaces Xent::EvalMasked (google/nnet/nnet-loss.cc:76-164) and the accumulators / Report() of class Xent
  * (nnet-loss.h:33-75, nnet-loss.cc:293-307).  net_out = the softmax outputs [num_frames x num_pdf] (device, row

@@ -11,7 +11,7 @@ There is no CPU fallback: importing works anywhere, but creating an engine witho
 library or without a B200 raises.
 """
 from .engine import Engine, EngineError, XentEngine, lib_path, load_library  # noqa: F401
-from .component import LstmProjectedStreams, NnetTrainOptions  # noqa: F401
-from .dispatch import StreamDispatcher  # noqa: F401
+from .component import LstmProjectedStreams, NnetTrainOptions, TimeShift  # noqa: F401
+from .dispatch import DeviceStreamDispatcher, StreamDispatcher  # noqa: F401
 from .loss import Xent, posterior_to_csr  # noqa: F401
 from . import nnet_io, parallel  # noqa: F401

@@ -47,6 +47,9 @@ class LstmProjectedStreams:
         self._device = device
         self._max_frames = int(max_frames)
         self._engine = None
+        # element-wise clip of the accumulated gradient in Update: None for the streams component, 50.0 for the
+        # standard single-stream LstmProjected (standard/nnet/nnet-lstm-projected.h:480-493)
+        self.max_grad_ = None
 
     # ---- Component surface ------------------------------------------------------------
     def GetType(self):
@@ -98,6 +101,7 @@ class LstmProjectedStreams:
         other = LstmProjectedStreams(self.input_dim_, self.output_dim_, self._device, self._max_frames)
         other.ncell_, other.nstream_ = self.ncell_, self.nstream_
         other.opts_ = NnetTrainOptions(self.opts_.learn_rate, self.opts_.momentum)
+        other.max_grad_ = self.max_grad_
         other._make_engine()
         other._engine.set_flat(0, self._engine.get_flat(0))
         other._engine.set_flat(1, self._engine.get_flat(1))
@@ -120,6 +124,8 @@ class LstmProjectedStreams:
         c = cls(comp.input_dim, comp.output_dim, device, max_frames)
         c.ncell_ = int(comp.attr("<CellDim>"))
         c.nstream_ = int(num_stream or comp.attr("<NumStream>") or 1)
+        if comp.type == "<LstmProjected>":
+            c.max_grad_ = 50.0   # the standard version clips in Update (nnet-lstm-projected.h:482)
         c._make_engine()
         c.SetParams(nnet_io.lstm_flat_params(comp))
         return c
@@ -182,7 +188,10 @@ class LstmProjectedStreams:
 
     def Update(self, input_=None, diff=None):
         # both arguments are unused by the reference too (LPS.h:501-512)
-        self._engine.update(self.opts_.learn_rate, self.opts_.momentum)
+        if self.max_grad_:
+            self._engine.update_clipped(self.opts_.learn_rate, self.opts_.momentum, self.max_grad_)
+        else:
+            self._engine.update(self.opts_.learn_rate, self.opts_.momentum)
 
     # Component::Propagate / Backpropagate (upstream nnet-component.h): size the output, then *Fnc
     def Propagate(self, in_):
@@ -204,3 +213,39 @@ class LstmProjectedStreams:
     @property
     def engine(self):
         return self._engine
+
+
+class TimeShift:
+    """Mirror of the standard version's TimeShift component (standard/nnet/nnet-time-shift.h): out row dst = in row
+    clamp(dst + shift, 0, rows - 1) as one device gather; Backpropagate is a no-op there (:53-56) and here."""
+    MARKER = "<TimeShift>"
+
+    def __init__(self, dim, shift=0):
+        self.input_dim_ = self.output_dim_ = int(dim)
+        self.shift_ = int(shift)
+
+    def GetType(self):
+        return "TimeShift"
+
+    def InitData(self, config):
+        toks = config.split()
+        i = 0
+        while i < len(toks):
+            if toks[i] == "<Shift>":
+                self.shift_ = int(toks[i + 1])
+                i += 2
+            else:
+                raise RuntimeError("Unknown token %s, a typo in config? (Shift)" % toks[i])   # nnet-time-shift.h:27-28
+
+    def PropagateFnc(self, in_, out):
+        from .engine import time_shift
+        time_shift(in_, out, self.shift_)
+
+    def Propagate(self, in_):
+        import torch
+        out = torch.empty_like(in_)
+        self.PropagateFnc(in_, out)
+        return out
+
+    def BackpropagateFnc(self, in_, out, out_diff, in_diff):
+        return None

@@ -149,7 +149,7 @@ __device__ __forceinline__ void stamp(int tag) {
   // thread 0 everywhere; in the TMA-fed loops also the sync / producer thread (256) and the MMA issuer's lane 0 (288)
   if ((threadIdx.x == 0 || ((threadIdx.x == 256 || threadIdx.x == 288) && tag >= 200)) && s_stamp_on) {
     int n = atomicAdd(&s_stamp_n, 1);
-    if (n < kMaxStamps) {
+    if ((unsigned)n < (unsigned)kMaxStamps) {
       s_stamp_log[2 * n] = tag;
       s_stamp_log[2 * n + 1] = clock64();
     }

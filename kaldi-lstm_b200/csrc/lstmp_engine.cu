@@ -73,7 +73,7 @@ struct lstmp_b200_engine {
   FwdTmaParams ftm{};
   BwdTmaParams btm{};
   size_t fwd_tma_smem = 0, bwd_tma_smem = 0;
-  __nv_bfloat16 *rhl = nullptr, *mhl = nullptr, *dghl = nullptr, *drhl = nullptr;
+  uint8_t *rhl = nullptr, *mhl = nullptr, *dghl = nullptr, *drhl = nullptr;
   int T_last = 0;        // frames of the last propagate (0 = none)
   bool have_bwd = false; // a backpropagate record exists for T_last
   unsigned long long launches = 0;
@@ -338,8 +338,12 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     return fail((int)e, "barrier counters: %s", cudaGetErrorString(e));
   }
   if (h->rec_tma) {
-    const size_t n_r = (size_t)2 * S * R, n_m = (size_t)2 * S * C, n_dg = (size_t)2 * S * 4 * C;
-    const size_t total = (2 * n_r + n_m + n_dg) * sizeof(__nv_bfloat16);
+    // exchange arrays: per group and 64-k chunk one tile image of roundup8(2*Sg) rows x 128 bytes; zero-initialised so
+    // that the k tail of the last chunk (never written) contributes nothing
+    const size_t tile = (size_t)((2 * h->ftm.Sg + 7) & ~7) * 128, G = (size_t)h->ftm.G;
+    const size_t n_r = G * h->ftm.nch_g * tile, n_m = G * h->ftm.nch_p * tile, n_dg = G * h->btm.nch_a * tile,
+                 n_dr = G * h->btm.nch_b * tile;
+    const size_t total = n_r + n_m + n_dg + n_dr;
     e = cudaMalloc((void**)&h->rhl, total);
     if (e == cudaSuccess) e = cudaMemset(h->rhl, 0, total);
     if (e != cudaSuccess) {
@@ -350,14 +354,6 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     h->dghl = h->mhl + n_m;
     h->drhl = h->dghl + n_dg;
     ws += total;
-    const int Sg = h->ftm.Sg;
-    const int halves = 2 * h->ftm.G;
-    if (make_hl_tensor_map(&h->ftm.tm_r, h->rhl, halves, Sg, R) || make_hl_tensor_map(&h->ftm.tm_m, h->mhl, halves, Sg, C) ||
-        make_hl_tensor_map(&h->btm.tm_dg, h->dghl, halves, Sg, 4 * C) ||
-        make_hl_tensor_map(&h->btm.tm_dr, h->drhl, halves, Sg, R)) {
-      lstmp_b200_destroy(h);
-      return fail(LSTMP_B200_EUNSUPPORTED, "cuTensorMapEncodeTiled failed for the hi/lo exchange arrays");
-    }
   }
   h->gemm_ws_floats = env_int("LSTMP_B200_SPLITK", 1) ? ((size_t)4 << 20) : 0;
   h->workspace_bytes = ws;
@@ -799,7 +795,19 @@ extern "C" int lstmp_b200_update(lstmp_b200_handle_t h, float learn_rate, float 
   CHECK_H(h);
   {
     Timed tm(h, 6, (cudaStream_t)stream);
-    CUDA_TRY(launch_update(h->params, h->corr, h->grads, h->nparams, learn_rate, momentum, (cudaStream_t)stream));
+    CUDA_TRY(launch_update(h->params, h->corr, h->grads, h->nparams, learn_rate, momentum, 0.f, (cudaStream_t)stream));
+  }
+  h->launches++;
+  return 0;
+}
+
+extern "C" int lstmp_b200_update_clipped(lstmp_b200_handle_t h, float learn_rate, float momentum, float max_grad,
+                                         void* stream) {
+  CHECK_H(h);
+  {
+    Timed tm(h, 6, (cudaStream_t)stream);
+    CUDA_TRY(launch_update(h->params, h->corr, h->grads, h->nparams, learn_rate, momentum, max_grad > 0.f ? max_grad : 0.f,
+                           (cudaStream_t)stream));
   }
   h->launches++;
   return 0;

@@ -1,6 +1,5 @@
 // Internal (non-ABI) interface between the host engine and the sm_100a kernels.
 #pragma once
-#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -98,28 +97,27 @@ cudaError_t fwd_tc_set_smem_limit(size_t bytes);
 cudaError_t launch_fwd_tc(const FwdTcParams& p, size_t smem_bytes, cudaStream_t stream);
 
 // ---- TMA-fed tcgen05 time loops, forward and backward (lstmp_recurrent_tma.cu) --------------------------------
-// One stream group (all S <= 64 streams).  Activations cross the chip as bf16 hi/lo pairs written by their producer
-// ([2*S rows x K] global arrays: rows 0..S-1 hi, S..2S-1 lo) and are pulled into a SWIZZLE_128B shared-memory ring by
-// cp.async.bulk.tensor through the tensor maps below; the CTA's weight slice is the stationary B operand.
+// Activations cross the chip as bf16 hi/lo pairs written by their producer into global "tile image" arrays (per 64-k
+// chunk the ready-made SWIZZLE_128B shared-memory image of [hi rows | lo rows]) and are pulled into a shared-memory
+// ring with one cp.async.bulk per chunk; the CTA's weight slice is the stationary B operand.
 struct FwdTmaParams {
   int I, C, R, S, T;
   int G, Sg, cpg;               // stream groups (own barrier each), streams per group, CTAs per group
   int nctas, cpc, rpc;          // CTA j of a group owns cells [j*cpc, +cpc) and r columns [j*rpc, +rpc)
   int n_g, n_p;                 // MMA N of the gate / projection products
   int nch_g, nch_p;             // 64-k chunks of the two contractions (K = R, K = C)
-  int nslot, stagger;
+  int nslot, nprod, stagger;
   unsigned chunk_g, chunk_p;    // bytes of one 64-k tile of the stationary weight slices
   unsigned off_bg, off_bp, off_ring, off_red, ldred, off_cprev, off_peep, off_bars;
   const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
   float *gifo, *cbuf, *hbuf, *mbuf, *rbuf, *out;
   long long ld_out;
   float *state_c, *state_r;
-  __nv_bfloat16 *rhl, *mhl;     // [G][2][Sg] x R, x C: hi/lo halves of the latest r / m
+  uint8_t *rhl, *mhl;           // [G][chunks][tile image]: bf16 hi/lo halves of the latest r / m (see store_hl)
   unsigned* bar;
   unsigned bar_base;
   int dbg;
   long long* dbg_stamps;
-  CUtensorMap tm_r, tm_m;
 };
 struct BwdTmaParams {
   int I, C, R, S, T;
@@ -128,7 +126,7 @@ struct BwdTmaParams {
   int cpc, rpb;
   int n_a, n_b;                 // MMA N of the d_r / d_m products
   int nch_a, nch_b;             // 64-k chunks: K = 4C (split over the kp ranks of a cluster), K = R
-  int nslot, stagger;
+  int nslot, nprod, stagger;
   unsigned chunk_a, chunk_b;
   unsigned off_ba, off_bb, off_ring, off_red, ldred, off_dgn, off_dcn, off_acc7, off_peep, off_bars;
   const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
@@ -137,16 +135,14 @@ struct BwdTmaParams {
   long long ld_od;
   float *dgifo, *dr;
   float* g_small;               // [G][7C] bias(4C) | peephole_i | peephole_f | peephole_o (G == 1: the gradient arena)
-  __nv_bfloat16 *dghl, *drhl;   // [G][2][Sg] x 4C, x R: hi/lo halves of the latest DGIFO / d_r
+  uint8_t *dghl, *drhl;         // [G][chunks][tile image]: bf16 hi/lo halves of the latest DGIFO / d_r
   unsigned* bar;
   unsigned bar_base;
   int dbg;
   long long* dbg_stamps;
-  CUtensorMap tm_dg, tm_dr;
 };
 bool fwd_tma_plan(int C, int R, int S, int G, int nctas, size_t smem_limit, FwdTmaParams* p, size_t* smem_bytes);
 bool bwd_tma_plan(int C, int R, int S, int G, int nctas, int kp, size_t smem_limit, BwdTmaParams* p, size_t* smem_bytes);
-int make_hl_tensor_map(void* out_map, const void* gptr, int halves, int Sg, int K);
 cudaError_t tma_set_smem_limits(size_t fwd_bytes, size_t bwd_bytes);
 int bwd_tma_max_ctas(int kp, size_t smem_bytes, int max_ctas);
 cudaError_t launch_fwd_tma(const FwdTmaParams& p, size_t smem_bytes, cudaStream_t stream);
@@ -160,8 +156,9 @@ cudaError_t launch_gemm(float* C, long long ldc, int M, int N, int K, float alph
                         cudaStream_t stream);
 
 // corr = G + momentum*corr ; param -= lr*corr   over the flat arena
+// clip > 0: corr is clamped element-wise to [-clip, clip] before the step (the standard/ component's gradient clip)
 cudaError_t launch_update(float* params, float* corr, const float* grads, size_t n, float lr, float momentum,
-                          cudaStream_t stream);
+                          float clip, cudaStream_t stream);
 // G[bias | p_i | p_f | p_o] = sum over groups of small_grads
 cudaError_t launch_small_grads(float* g_small /*7C contiguous in the arena*/, const float* small, int ngroups,
                                int n7c, cudaStream_t stream);

@@ -95,7 +95,7 @@ cudaError_t launch_gemm_simt(float* C, long long ldc, int M, int N, int K, float
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) update_kernel(float4* __restrict__ params, float4* __restrict__ corr,
                                                      const float4* __restrict__ grads, size_t n4, float lr,
-                                                     float momentum) {
+                                                     float momentum, float clip) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
@@ -104,6 +104,12 @@ __global__ void __launch_bounds__(256) update_kernel(float4* __restrict__ params
     c.y = fmaf(momentum, c.y, g.y);
     c.z = fmaf(momentum, c.z, g.z);
     c.w = fmaf(momentum, c.w, g.w);
+    if (clip > 0.f) {  // standard/nnet/nnet-lstm-projected.h:469-493: element-wise clamp of the accumulated gradient
+      c.x = fminf(fmaxf(c.x, -clip), clip);
+      c.y = fminf(fmaxf(c.y, -clip), clip);
+      c.z = fminf(fmaxf(c.z, -clip), clip);
+      c.w = fminf(fmaxf(c.w, -clip), clip);
+    }
     w.x = fmaf(-lr, c.x, w.x);
     w.y = fmaf(-lr, c.y, w.y);
     w.z = fmaf(-lr, c.z, w.z);
@@ -114,13 +120,13 @@ __global__ void __launch_bounds__(256) update_kernel(float4* __restrict__ params
 }
 
 cudaError_t launch_update(float* params, float* corr, const float* grads, size_t n, float lr, float momentum,
-                          cudaStream_t stream) {
+                          float clip, cudaStream_t stream) {
   size_t n4 = n / 4;  // arena length is a multiple of 4 (C % 4 == 0)
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   update_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(corr),
-                                            reinterpret_cast<const float4*>(grads), n4, lr, momentum);
+                                            reinterpret_cast<const float4*>(grads), n4, lr, momentum, clip);
   return cudaGetLastError();
 }
 

@@ -21,8 +21,8 @@
 // a-th K slice (TMA gather of 4C/kp columns of DGIFO(t+1) only) and the kp partial [S x R/np] blocks are summed through
 // distributed shared memory (a cluster barrier, not a grid barrier).  d_m(t) = d_r(t) * W_r_m and the derivative
 // chain run cell-sliced over all CTAs as in forward.  Two grid barriers per timestep in both directions.
-#include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "lstmp_common.cuh"
@@ -44,14 +44,6 @@ struct Pipe {
   uint32_t acc;  // products finished so far (phase of the accumulator-ready barrier)
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
-          "r"(smem_dst),
-      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n"
@@ -108,10 +100,12 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t ran
 // fence.proxy.async adds a MEMBAR.ALL.GPU); gpu-scope ordering itself comes from the grid barrier's release / acquire
 __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
 
+__device__ __forceinline__ void tma_bulk_g2s_u32(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar);
+
 struct Ring {
   uint8_t* ring;
   uint64_t *full, *empty, *accum, *gridok;
-  int nslot;
+  int nslot, nprod;
 };
 
 // Grid barrier between the co-resident CTAs of one stream group, split into arrive / wait and run by ONE thread per
@@ -149,26 +143,31 @@ constexpr int kProducerWarp = 8, kIssuerWarp = 9;
 __device__ __forceinline__ bool is_sync_thread() { return threadIdx.x == kProducerWarp * 32; }
 
 // red[row*ldred + n] = D[row][n] + D[row][nh + n] for the 128 stacked rows, n < nvalid, where
-// D = A * B^T over K = 64*nch:  A = boxes [2 halves x Sg x 64] of the global bf16 array behind `tmap` (halves half0 =
-// hi, half0 + 1 = lo), columns (kc0 + chunk)*64; B = the stationary tiles b_addr + chunk * chunk_b.  Chunks are walked in
+// D = A * B^T over K = 64*nch:  A = the tile images (kc0 + chunk) of the global exchange array `img` (each the
+// ready-made SWIZZLE_128B shared-memory image of [hi rows | lo rows] x 64 k, written by the producers of the
+// activation, see store_hl); B = the stationary tiles b_addr + chunk * chunk_b.  Chunks are walked in
 // the rotated order chunk = (c + rot) mod nch (order-independent sum up to fp32 rounding, fixed per CTA:
 // bit-reproducible; spreads the CTAs' requests for the same lines over time).  grid_wait: the operand was written by
 // other CTAs before the grid barrier this CTA last arrived at -- the producer waits for it before its first copy.
 // Every thread of the CTA calls this (CTA-uniform arguments); contains one __syncthreads at the end.
 __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& gs, bool grid_wait,
-                                            const CUtensorMap* tmap, int Sg, int half0, int kc0, int nch, int rot,
+                                            const uint8_t* img, int Sg, int kc0, int nch, int rot,
                                             uint32_t b_addr, uint32_t chunk_b, uint32_t idesc, uint32_t tmem_d, int nh,
                                             int nvalid, float* red, int ldred) {
   // warp index through a shuffle: provably warp-uniform for ptxas (UMMA operands stay in uniform registers)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int nslot = rg.nslot;
   uint32_t slot = ps.cc % (uint32_t)nslot, use = ps.cc / (uint32_t)nslot;
+  // With fewer ring slots than producers a producer could lap the parity of a slot's "empty" barrier (it would test
+  // the phase two uses back): never more producers than slots.
+  const int nprod = nslot < rg.nprod ? nslot : rg.nprod;
   const int prod = warp == kProducerWarp ? 0 : warp == kProducerWarp + 2 ? 1 : warp == kProducerWarp + 3 ? 2 : -1;
-  if (prod >= 0) {
+  if (prod >= 0 && prod < nprod) {
     // ------------------------------ TMA producers --------------------------------------------
-    // One 3-D box [2 halves][Sg rows][64 k] = one copy per chunk.  A copy costs its issuing thread ~150-200 cycles
-    // whatever its size (measured: 380 cycles per chunk with two 2-D copies from one thread), so the chunks are dealt
-    // round-robin to three threads in three warps.
+    // One 1-D bulk copy (cp.async.bulk, SASS UBLKCP) per chunk: the global array already holds the swizzled tile
+    // image.  Tensor-map copies (cp.async.bulk.tensor, 2-D / 3-D boxes of 128-byte rows) were measured first and
+    // delivered one row per ~3.5 cycles (36-43 B/clk per SM, profiles/r2_stamps_*_tensormap.txt), below what L2 gives
+    // this all-gather pattern.  The chunks are dealt round-robin to three threads in three warps.
     if (lane == 0) {
       if (grid_wait) {
         if (prod == 0) {
@@ -180,12 +179,13 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& 
       }
       const uint32_t ring_s = smem_u32(rg.ring);
       const uint32_t bytes = (uint32_t)(2 * Sg * 128);
-      for (int c = prod; c < nch; c += NPROD) {
+      const uint32_t tile_bytes = (uint32_t)(((2 * Sg + 7) & ~7) * 128);
+      for (int c = prod; c < nch; c += nprod) {
         const uint32_t idx = ps.cc + (uint32_t)c, sl = idx % (uint32_t)nslot, us = idx / (uint32_t)nslot;
         if (us > 0) mbar_wait(&rg.empty[sl], (us - 1) & 1);
         const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
         mbar_arrive_expect_tx(&rg.full[sl], bytes);
-        tma_load_3d(ring_s + sl * SLOT_BYTES, tmap, (kc0 + ce) * KC, 0, half0, &rg.full[sl]);
+        tma_bulk_g2s_u32(ring_s + sl * SLOT_BYTES, img + (size_t)(kc0 + ce) * tile_bytes, bytes, &rg.full[sl]);
       }
       stamp(203);
     }
@@ -247,11 +247,20 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& 
   ps.acc += 1;
 }
 
-__device__ __forceinline__ void store_hl(__nv_bfloat16* base, int Sg, size_t ld, int s, int col, float v) {
+// Element (stream s, column col) of an activation -> the hi / lo bf16 halves inside the tile image of chunk col / 64:
+// row s (hi) and Sg + s (lo), 16-byte unit (col % 64) / 8 XOR-swizzled with the row (tc::sw128_off).
+__device__ __forceinline__ void store_hl(uint8_t* img, int Sg, uint32_t tile_bytes, int s, int col, float v) {
   __nv_bfloat16 h, l;
   split_bf16(v, h, l);
-  base[(size_t)s * ld + col] = h;
-  base[(size_t)(Sg + s) * ld + col] = l;
+  const int kk = col & (KC - 1);
+  uint8_t* t = img + (size_t)(col / KC) * tile_bytes + (kk & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(t + tc::sw128_off(s, kk >> 3)) = h;
+  *reinterpret_cast<__nv_bfloat16*>(t + tc::sw128_off(Sg + s, kk >> 3)) = l;
+}
+__device__ __forceinline__ void tma_bulk_g2s_u32(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 }  // namespace tm
 
@@ -276,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
   rg.accum = bars + 2 * MAX_SLOTS;
   rg.gridok = bars + 2 * MAX_SLOTS + 1;
   rg.nslot = p.nslot;
+  rg.nprod = p.nprod;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -287,9 +297,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
   const int nc = max(0, min(cpc, C - c0));  // my cells
   const int r0 = j * rpc;
   const int nr = max(0, min(rpc, R - r0));  // my projection outputs
-  const int row_hi = grp * 2 * Sg;          // first row of my group's hi block in the [G][2][Sg][K] exchange arrays
-  __nv_bfloat16* rhl = p.rhl + (size_t)row_hi * R;
-  __nv_bfloat16* mhl = p.mhl + (size_t)row_hi * C;
+  // my group's tile images in the exchange arrays [G][chunks][tile]
+  const uint32_t tile_bytes = (uint32_t)(((2 * Sg + 7) & ~7) * 128);
+  uint8_t* rhl = p.rhl + (size_t)grp * p.nch_g * tile_bytes;
+  uint8_t* mhl = p.mhl + (size_t)grp * p.nch_p * tile_bytes;
 
   if (tid == 0) {
     for (int s = 0; s < p.nslot; ++s) {
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
     int s = idx / nr, n = idx - s * nr;
     float v = p.state_r[(size_t)(s_base + s) * R + r0 + n];
     p.rbuf[(size_t)(s_base + s) * R + r0 + n] = v;
-    store_hl(rhl, Sg, (size_t)R, s, r0 + n, v);
+    store_hl(rhl, Sg, tile_bytes, s, r0 + n, v);
   }
   for (int cl = tid; cl < nc; cl += kThreads) {
     peep[cl] = p.p_i[c0 + cl];
@@ -372,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
   gs.nctas = (unsigned)p.cpg;
   gs.off = (p.dbg & 1) != 0;
   stamp_begin((p.dbg & 4) && blockIdx.x == 0);
+  __syncthreads();
   if (is_sync_thread()) gs.arrive();  // r_0 hi/lo of this CTA is in place
   stamp(1);
   Pipe ps{0u, 0u};
@@ -391,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
         xo = gp[3 * C];
       }
       // gifo(t) += r(t-1) * W_gifo_r^T                                       (LPS.h:275)
-      tma_product(ps, rg, gs, true, &p.tm_r, Sg, 2 * grp, 0, p.nch_g, rot_g, bg_s, p.chunk_g, idesc_g, tmem_base + COL_A,
+      tma_product(ps, rg, gs, true, rhl, Sg, 0, p.nch_g, rot_g, bg_s, p.chunk_g, idesc_g, tmem_base + COL_A,
                   4 * cpc, 4 * nc, red, ldred);
       stamp(11);
       // pass 1: the cell update; only m(t) hi/lo -- what the other CTAs wait for -- is stored before the arrive
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
         float ao = (rh[3 * nc] + rl[3 * nc]) + xo + c * po;   // :303  (uses c(t), post-clip)
         float go = sigmoidf_fast(ao);                         // :306
         float m = h * go;                                     // :309
-        store_hl(mhl, Sg, (size_t)C, s, c0 + cl, m);
+        store_hl(mhl, Sg, tile_bytes, s, c0 + cl, m);
         cprev[idx] = c;
         // the record goes to HBM after the arrive (pass 2); park it in the consumed accumulator block meanwhile
         rh[0] = gg; rh[nc] = gi; rh[2 * nc] = gf; rh[3 * nc] = go;
@@ -453,13 +465,13 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
     }
     // ================= phase 2: projection r(t) = m(t) * W_r_m^T for my columns (LPS.h:312) ==
     if (nr > 0) {
-      tma_product(ps, rg, gs, true, &p.tm_m, Sg, 2 * grp, 0, p.nch_p, rot_p, bp_s, p.chunk_p, idesc_p, tmem_base + COL_B,
+      tma_product(ps, rg, gs, true, mhl, Sg, 0, p.nch_p, rot_p, bp_s, p.chunk_p, idesc_p, tmem_base + COL_B,
                   rpc, nr, red, ldred);
       stamp(22);
       for (int idx = tid; idx < Sg * nr; idx += kThreads) {
         int s = idx / nr, n = idx - s * nr;
         float v = red[s * ldred + n] + red[(Sg + s) * ldred + n];
-        store_hl(rhl, Sg, (size_t)R, s, r0 + n, v);
+        store_hl(rhl, Sg, tile_bytes, s, r0 + n, v);
         red[s * ldred + n] = v;
       }
       fence_async_global();
@@ -519,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
   rg.accum = bars + 2 * MAX_SLOTS;
   rg.gridok = bars + 2 * MAX_SLOTS + 1;
   rg.nslot = p.nslot;
+  rg.nprod = p.nprod;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -532,9 +545,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
   const int nn = max(0, min(rpb, R - n0));
   const int c0 = j * cpc;
   const int nc = max(0, min(cpc, C - c0));  // my cells
-  const int row_hi = grp * 2 * Sg;
-  __nv_bfloat16* dghl = p.dghl + (size_t)row_hi * 4 * C;
-  __nv_bfloat16* drhl = p.drhl + (size_t)row_hi * R;
+  const uint32_t tile_bytes = (uint32_t)(((2 * Sg + 7) & ~7) * 128);
+  uint8_t* dghl = p.dghl + (size_t)grp * p.nch_a * tile_bytes;
+  uint8_t* drhl = p.drhl + (size_t)grp * p.nch_b * tile_bytes;
   // my K slice of the 4C contraction, in 64-column chunks
   const int kbase = p.nch_a / kp, krem = p.nch_a % kp;
   const int ks = a * kbase + min(a, krem);
@@ -632,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       }
       if (have_next) {
         if (nka > 0) {
-          tma_product(ps, rg, gs, true, &p.tm_dg, Sg, 2 * grp, ks, nka, rot_a, ba_s, p.chunk_a, idesc_a,
+          tma_product(ps, rg, gs, true, dghl, Sg, ks, nka, rot_a, ba_s, p.chunk_a, idesc_a,
                       tmem_base + COL_A, rpb, nn, red, ldred);
         } else {
           if (is_sync_thread()) gs.wait();
@@ -659,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
 #pragma unroll
           for (int q = 0; q < 8; ++q) v += ph[q] + pl[q];
         }
-        store_hl(drhl, Sg, (size_t)R, s, n0 + n, v);
+        store_hl(drhl, Sg, tile_bytes, s, n0 + n, v);
         p.dr[row * R + n0 + n] = v;
       }
       fence_async_global();
@@ -683,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
         yh = p.hbuf[row * C + c0 + cl];
         yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;
       }
-      tma_product(ps, rg, gs, true, &p.tm_dr, Sg, 2 * grp, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b,
+      tma_product(ps, rg, gs, true, drhl, Sg, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b,
                   tmem_base + COL_B, cpc, nc, red, ldred);
       stamp(45);
       for (int idx = tid; idx < Sg * nc; idx += kThreads) {
@@ -710,10 +723,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
         float d_i = (d_c * yg) * yi * (1.0f - yi);            // :435-436
         float d_g = (d_c * yi) * (1.0f - yg * yg);            // :439-440
         // DGIFO(t) hi/lo is what the other CTAs wait for; the fp32 record is stored after the arrive
-        store_hl(dghl, Sg, (size_t)4 * C, s, c0 + cl, d_g);
-        store_hl(dghl, Sg, (size_t)4 * C, s, C + c0 + cl, d_i);
-        store_hl(dghl, Sg, (size_t)4 * C, s, 2 * C + c0 + cl, d_f);
-        store_hl(dghl, Sg, (size_t)4 * C, s, 3 * C + c0 + cl, d_o);
+        store_hl(dghl, Sg, tile_bytes, s, c0 + cl, d_g);
+        store_hl(dghl, Sg, tile_bytes, s, C + c0 + cl, d_i);
+        store_hl(dghl, Sg, tile_bytes, s, 2 * C + c0 + cl, d_f);
+        store_hl(dghl, Sg, tile_bytes, s, 3 * C + c0 + cl, d_o);
         dgn[idx] = d_i;
         dgn[Sg * cpc + idx] = d_f;
         dcn[idx] = d_c;
@@ -774,6 +787,16 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
 // host side
 // ------------------------------------------------------------------------------------------------
 static size_t round1k(size_t b) { return (b + 1023) & ~size_t(1023); }
+static int num_producers() {  // LSTMP_B200_TMA_PRODUCERS: 1..3 producer warps (default 3)
+  const char* v = getenv("LSTMP_B200_TMA_PRODUCERS");
+  const int n = (v && *v) ? atoi(v) : tm::NPROD;
+  return n < 1 ? 1 : n > tm::NPROD ? tm::NPROD : n;
+}
+static int max_slots() {  // LSTMP_B200_TMA_SLOTS caps the ring depth (tests: the 2-slot ring of the tightest shapes)
+  const char* v = getenv("LSTMP_B200_TMA_SLOTS");
+  const int n = (v && *v) ? atoi(v) : tm::MAX_SLOTS;
+  return n < 2 ? 2 : n > tm::MAX_SLOTS ? tm::MAX_SLOTS : n;
+}
 
 bool fwd_tma_plan(int C, int R, int S, int G, int nctas, size_t smem_limit, FwdTmaParams* p, size_t* smem_bytes) {
   using namespace tm;
@@ -813,8 +836,9 @@ bool fwd_tma_plan(int C, int R, int S, int G, int nctas, size_t smem_limit, FwdT
   const size_t reserve = 1024 /* base alignment */ + (size_t)static_smem_reserve();
   if (smem_limit < off + tail + reserve + (size_t)2 * SLOT_BYTES) return false;
   int nslot = (int)((smem_limit - off - tail - reserve) / SLOT_BYTES);
-  if (nslot > MAX_SLOTS) nslot = MAX_SLOTS;
+  if (nslot > max_slots()) nslot = max_slots();
   p->nslot = nslot;
+  p->nprod = num_producers();
   off += (size_t)nslot * SLOT_BYTES;
   p->off_red = take((size_t)128 * ldred * 4);
   p->off_cprev = take((size_t)Sg * cpc * 4);
@@ -864,8 +888,9 @@ bool bwd_tma_plan(int C, int R, int S, int G, int nctas, int kp, size_t smem_lim
   const size_t reserve = 1024 + (size_t)static_smem_reserve();
   if (smem_limit < off + tail + reserve + (size_t)2 * SLOT_BYTES) return false;
   int nslot = (int)((smem_limit - off - tail - reserve) / SLOT_BYTES);
-  if (nslot > MAX_SLOTS) nslot = MAX_SLOTS;
+  if (nslot > max_slots()) nslot = max_slots();
   p->nslot = nslot;
+  p->nprod = num_producers();
   off += (size_t)nslot * SLOT_BYTES;
   p->off_red = take((size_t)128 * ldred * 4);
   p->off_dgn = take((size_t)2 * Sg * cpc * 4);
@@ -875,31 +900,6 @@ bool bwd_tma_plan(int C, int R, int S, int G, int nctas, int kp, size_t smem_lim
   p->off_bars = take(256);
   *smem_bytes = off + 1024;
   return *smem_bytes + (size_t)static_smem_reserve() <= smem_limit;
-}
-
-// [group][hi|lo][Sg] x K bf16 array -> 3-D tensor map with [2 halves][Sg rows][64 k] boxes, 128-byte swizzle, zero
-// fill outside (the K tail of the last box).  cuTensorMapEncodeTiled is resolved through the runtime (no link against libcuda).
-int make_hl_tensor_map(void* out_map, const void* gptr, int halves, int Sg, int K) {
-  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) return -1;
-    fn = (encode_fn)sym;
-  }
-  // dims (fastest first): k, stream within the half, half index (2*group + {hi, lo}); box = [2 halves][Sg][64 k]
-  const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)Sg, (cuuint64_t)halves};
-  const cuuint64_t gstride[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * (cuuint64_t)Sg};
-  const cuuint32_t box[3] = {(cuuint32_t)tm::KC, (cuuint32_t)Sg, 2u};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr),
-                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
 cudaError_t tma_set_smem_limits(size_t fwd_bytes, size_t bwd_bytes) {

@@ -17,6 +17,9 @@ ABI_SYMBOLS = [
     "lstmp_b200_timing_enable", "lstmp_b200_timing_read", "lstmp_b200_debug_gemm",
     "lstmp_b200_xent_create", "lstmp_b200_xent_destroy", "lstmp_b200_xent_eval_masked",
     "lstmp_b200_xent_get_stats", "lstmp_b200_xent_reset_stats",
+    "lstmp_b200_update_clipped", "lstmp_b200_time_shift",
+    "lstmp_b200_dispatch_create", "lstmp_b200_dispatch_destroy", "lstmp_b200_dispatch_set_transform",
+    "lstmp_b200_dispatch_load_utt", "lstmp_b200_dispatch_assemble", "lstmp_b200_dispatch_get_stats",
 ]
 
 TIMING_KINDS = ["input_gemm", "fwd_recurrent", "bwd_recurrent", "in_diff_gemm", "wgrad_gemms", "small_grads",
@@ -84,6 +87,8 @@ def load_library():
     L.lstmp_b200_backpropagate.argtypes = [vp, vp, sz, vp, sz, vp, sz, ci, vp]
     L.lstmp_b200_update.argtypes = [vp, fp, fp, vp]
     L.lstmp_b200_allreduce_grads_nccl.argtypes = [vp, vp, vp]
+    L.lstmp_b200_update_clipped.argtypes = [vp, fp, fp, fp, vp]
+    L.lstmp_b200_time_shift.argtypes = [vp, sz, vp, sz, ci, ci, ci, vp]
     L.lstmp_b200_get_info.argtypes = [vp, ctypes.POINTER(Info)]
     L.lstmp_b200_get_record.argtypes = [vp, ci, vp, sz, vp]
     L.lstmp_b200_debug_gemm.argtypes = [ci, vp, sz, ci, ci, ci, fp, vp, sz, ci, vp, sz, ci, fp, vp, vp]
@@ -237,6 +242,11 @@ class Engine:
     def update(self, learn_rate, momentum):
         _chk(load_library().lstmp_b200_update(self._h, float(learn_rate), float(momentum), self._stream()))
 
+    def update_clipped(self, learn_rate, momentum, max_grad):
+        """Update with the element-wise clip of the standard single-stream component (nnet-lstm-projected.h:480-493)."""
+        _chk(load_library().lstmp_b200_update_clipped(self._h, float(learn_rate), float(momentum), float(max_grad),
+                                                      self._stream()))
+
     def allreduce_grads_nccl(self, comm_ptr, stream_ptr=None):
         """Sum all-reduce of the fresh-gradient arena over the raw ncclComm_t `comm_ptr` on `stream_ptr` (a
         cudaStream_t as int; default: the current stream)."""
@@ -274,6 +284,16 @@ def debug_gemm(backend, C, M, N, K, alpha, A, tA, B, tB, beta=0.0, bias=None):
                                  ctypes.c_void_p(A.data_ptr()), A.stride(0), int(tA), ctypes.c_void_p(B.data_ptr()),
                                  B.stride(0), int(tB), float(beta),
                                  ctypes.c_void_p(bias.data_ptr()) if bias is not None else None, st))
+
+
+def time_shift(x, out, shift):
+    """out row dst = x row clamp(dst + shift, 0, rows - 1) on the device (TimeShift::PropagateFnc)."""
+    px, ldx = Engine._mat(x, x.shape[1], "in")
+    po, ldo = Engine._mat(out, x.shape[1], "out")
+    if out.shape[0] != x.shape[0]:
+        raise EngineError(EINVAL, "out rows != in rows")
+    _chk(load_library().lstmp_b200_time_shift(px, ldx, po, ldo, x.shape[0], x.shape[1], int(shift),
+                                              _cur_stream(x.device.index or 0)))
 
 
 class XentEngine:

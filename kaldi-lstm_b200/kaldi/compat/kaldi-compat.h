@@ -36,6 +36,11 @@ struct KaldiErr {
   [[noreturn]] ~KaldiErr() noexcept(false) { throw std::runtime_error(os.str()); }
 };
 #define KALDI_ERR ::kaldi::KaldiErr().os
+struct KaldiWarn {
+  std::ostringstream os;
+  ~KaldiWarn() { std::cerr << "WARNING " << os.str() << std::endl; }
+};
+#define KALDI_WARN ::kaldi::KaldiWarn().os
 #define KALDI_ASSERT(cond)                                                            \
   do {                                                                                \
     if (!(cond)) throw std::runtime_error(std::string("KALDI_ASSERT failed: ") + #cond); \

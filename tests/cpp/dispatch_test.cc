@@ -1,0 +1,163 @@
+// Test driver: kaldi/b200-stream-dispatch.h (device-side chunk assembly behind the C ABI) against a literal host
+// restatement of the reference trainer's loop (google/nnetbin/bd-nnet-train-lstm-streams.cc:128-212), bit-exact:
+// feat (after AddShift + Rescale), frame_mask, target, new_utt_flags of every chunk; plus the TimeShift row gather.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "b200-stream-dispatch.h"
+
+using namespace kaldi;
+using namespace kaldi::nnet1;
+
+struct Utt {
+  std::string key;
+  Matrix<BaseFloat> feats;
+};
+// the two table-reader concepts of the trainer, in memory
+struct SeqReader {
+  const std::vector<Utt>* u;
+  size_t i;
+  bool Done() const { return i >= u->size(); }
+  const std::string& Key() const { return (*u)[i].key; }
+  const Matrix<BaseFloat>& Value() const { return (*u)[i].feats; }
+  void Next() { ++i; }
+};
+struct TgtReader {
+  std::map<std::string, Posterior> m;
+  bool HasKey(const std::string& k) const { return m.count(k) != 0; }
+  const Posterior& Value(const std::string& k) const { return m.at(k); }
+};
+
+struct Chunk {
+  Matrix<BaseFloat> feat;
+  std::vector<float> mask;
+  Posterior target;
+  std::vector<int> flags;
+};
+
+// literal restatement of TRAIN.cc:143-212 on the host (feature transform = AddShift then Rescale)
+static std::vector<Chunk> reference_loop(const std::vector<Utt>& utts, const TgtReader& tr, int S, int T, int delay, int D,
+                                         const std::vector<float>& shift, const std::vector<float>& scale) {
+  SeqReader fr{&utts, 0};
+  std::vector<std::string> keys(S);
+  std::vector<Matrix<BaseFloat> > feats(S);
+  std::vector<Posterior> targets(S);
+  std::vector<int> curt(S, 0), lent(S, 0), flags(S, 0);
+  std::vector<Chunk> out;
+  while (1) {
+    for (int s = 0; s < S; s++) {
+      if (curt[s] < lent[s]) { flags[s] = 0; continue; }
+      while (!fr.Done()) {
+        keys[s] = fr.Key();
+        feats[s] = fr.Value();
+        if (!tr.HasKey(keys[s])) { fr.Next(); continue; }
+        targets[s] = tr.Value(keys[s]);
+        if (feats[s].NumRows() != (int)targets[s].size()) { fr.Next(); continue; }
+        curt[s] = 0; lent[s] = feats[s].NumRows(); flags[s] = 1;
+        fr.Next();
+        break;
+      }
+    }
+    int done = 1;
+    for (int s = 0; s < S; s++) if (curt[s] < lent[s]) done = 0;
+    if (done) break;
+    Chunk c;
+    c.feat.Resize(T * S, D);
+    c.mask.assign(T * S, 0.f);
+    c.target.resize(T * S);
+    for (int t = 0; t < T; t++)
+      for (int s = 0; s < S; s++) {
+        if (lent[s] == 0) { curt[s]++; continue; }
+        if (curt[s] < lent[s]) { c.mask[t * S + s] = 1; c.target[t * S + s] = targets[s][curt[s]]; }
+        else { c.mask[t * S + s] = 0; c.target[t * S + s] = targets[s][lent[s] - 1]; }
+        int src = (curt[s] + delay < lent[s]) ? curt[s] + delay : lent[s] - 1;
+        for (int d = 0; d < D; d++) {
+          volatile float v = feats[s](src, d) + shift[d];   // AddShift, then Rescale: two roundings, as two components
+          c.feat(t * S + s, d) = v * scale[d];
+        }
+        curt[s]++;
+      }
+    c.flags = flags;
+    out.push_back(c);
+  }
+  return out;
+}
+
+int main() {
+  try {
+    const int S = 5, T = 7, delay = 3, D = 8, NU = 23;
+    std::mt19937 rng(7);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<Utt> utts(NU);
+    TgtReader tr;
+    for (int i = 0; i < NU; i++) {
+      int L = 1 + (int)(rng() % 40);
+      utts[i].key = "utt" + std::to_string(i);
+      utts[i].feats.Resize(L, D);
+      for (int r = 0; r < L; r++)
+        for (int d = 0; d < D; d++) utts[i].feats(r, d) = nd(rng);
+      if (i % 6 == 2) continue;                       // missing targets
+      Posterior p(i % 6 == 4 ? L - 1 : L);            // length mismatch every 6th
+      for (size_t r = 0; r < p.size(); r++) p[r].push_back(std::make_pair((int32)(rng() % 50), 1.0f));
+      tr.m[utts[i].key] = p;
+    }
+    std::vector<float> shift(D), scale(D);
+    for (int d = 0; d < D; d++) { shift[d] = nd(rng) * 10.f; scale[d] = 0.2f + 0.01f * d; }
+    std::vector<Chunk> ref = reference_loop(utts, tr, S, T, delay, D, shift, scale);
+
+    B200StreamDispatch disp(S, T, delay, D, 64);
+    Vector<BaseFloat> vs(D), vc(D);
+    for (int d = 0; d < D; d++) { vs(d) = shift[d]; vc(d) = scale[d]; }
+    disp.SetTransform(&vs, &vc);
+    SeqReader fr{&utts, 0};
+    CuMatrix<BaseFloat> feat;
+    Vector<BaseFloat> mask;
+    Posterior target;
+    std::vector<int32> flags;
+    size_t n = 0;
+    long long bad = 0;
+    while (disp.NextChunk(&fr, &tr, &feat, &mask, &target, &flags)) {
+      if (n >= ref.size()) { printf("FAIL: more chunks than the reference loop\n"); return 1; }
+      Matrix<BaseFloat> host;
+      CU_SAFE_CALL(cudaDeviceSynchronize());
+      feat.CopyToMat(&host);
+      const Chunk& c = ref[n];
+      for (int r = 0; r < T * S; r++) {
+        for (int d = 0; d < D; d++)
+          if (host(r, d) != c.feat(r, d)) bad++;
+        if (mask(r) != c.mask[r]) bad++;
+        if (target[r] != c.target[r]) bad++;
+      }
+      for (int s = 0; s < S; s++)
+        if (flags[s] != c.flags[s]) bad++;
+      n++;
+    }
+    if (n != ref.size() || bad) { printf("FAIL: %zu chunks vs %zu, %lld mismatches\n", n, ref.size(), bad); return 1; }
+    lstmp_b200_dispatch_stats_t st = disp.Stats();
+    printf("dispatch: %zu chunks bit-exact, %llu utterances uploaded once (%llu bytes H2D in total, %.0f per chunk)\n", n,
+           st.utterances_loaded, st.h2d_bytes, (double)st.h2d_bytes / (double)n);
+
+    // TimeShift
+    Matrix<BaseFloat> hin(11, 6), hout;
+    for (int r = 0; r < 11; r++) for (int d = 0; d < 6; d++) hin(r, d) = nd(rng);
+    CuMatrix<BaseFloat> din(hin), dout(11, 6);
+    for (int shiftv : {5, -3, 0, 40}) {
+      B200TimeShiftPropagate(din, shiftv, &dout);
+      CU_SAFE_CALL(cudaDeviceSynchronize());
+      dout.CopyToMat(&hout);
+      for (int r = 0; r < 11; r++) {
+        int src = r + shiftv; src = src < 0 ? 0 : src; src = src > 10 ? 10 : src;
+        for (int d = 0; d < 6; d++) if (hout(r, d) != hin(src, d)) { printf("FAIL: time shift %d\n", shiftv); return 1; }
+      }
+    }
+    printf("PASS\n");
+    return 0;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "dispatch_test: %s\n", e.what());
+    return 2;
+  }
+}

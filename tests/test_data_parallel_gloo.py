@@ -106,3 +106,73 @@ def test_shard_streams_requires_divisibility():
     assert klb.parallel.shard_streams(256, 3, 8) == (96, 128)
     with pytest.raises(ValueError):
         klb.parallel.shard_streams(10, 0, 4)
+
+
+# ---- lock-step termination with uneven shards ----------------------------------------------------
+def _uneven_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle_py
+    import kaldi_lstm_b200 as klb
+    flat = oracle_py.init_params(I, C, R, 0.3, 77)
+    lo, hi = klb.parallel.shard_streams(S, rank, world)
+    Sl = hi - lo
+    layer = OracleLayer(oracle_py, Sl, flat)
+    trainer = klb.parallel.StreamShardTrainer([layer])
+    xs, ods = _data()
+    my_chunks = NCHUNK if rank == 0 else NCHUNK - 1          # rank 1 runs out of data one chunk early
+    it = iter(range(my_chunks))
+
+    def next_chunk():
+        n = next(it, None)
+        if n is None:
+            return None
+        x = torch.from_numpy(np.ascontiguousarray(xs[n][:, lo:hi]).reshape(T * Sl, I))
+        od = torch.from_numpy(np.ascontiguousarray(ods[n][:, lo:hi]).reshape(T * Sl, R))
+        return x, od, None
+
+    def padding_chunk():                                      # all-padding: zero features, zero loss gradient
+        return torch.zeros(T * Sl, I), torch.zeros(T * Sl, R), None
+
+    counts = trainer.run(next_chunk, lambda out, od: od, padding_chunk)
+    q.put((rank, layer.o.get_params(), counts))
+    dist.destroy_process_group()
+
+
+def test_uneven_shards_terminate_in_lock_step():
+    """Ranks run out of data after different numbers of chunks; every chunk carries a collective.  The rank that is
+    done keeps stepping on all-padding chunks until every rank is done -- nobody blocks in the all-reduce, and the
+    result equals the single-process run in which the exhausted streams are padded (TRAIN.cc:190-202)."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle_py
+    oracle_py.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_uneven_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res = {r: (prm, cnt) for r, prm, cnt in got}
+    assert res[0][1] == (NCHUNK, 0) and res[1][1] == (NCHUNK - 1, 1)
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    flat = oracle_py.init_params(I, C, R, 0.3, 77)
+    o = oracle_py.Oracle(I, C, R, S, np.float32)
+    o.set_params(flat)
+    xs, ods = _data()
+    half = S // 2
+    for n in range(NCHUNK):
+        x, od = xs[n].copy(), ods[n].copy()
+        if n == NCHUNK - 1:                                   # rank 1's streams are exhausted: padded rows
+            x[:, half:] = 0
+            od[:, half:] = 0
+        o.propagate(x.reshape(T * S, I))
+        o.backpropagate(x.reshape(T * S, I), od.reshape(T * S, R), MMT)
+        o.update(LR)
+    ref = o.get_params()
+    assert np.abs(res[0][0] - ref).max() <= 1e-5 * np.abs(ref).max()

@@ -20,7 +20,7 @@ def _data():
     return xs, ods
 
 
-def _run(rank, world, port, q):
+def _run(rank, world, port, q, c_path=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     import kaldi_lstm_b200 as klb
@@ -33,7 +33,9 @@ def _run(rank, world, port, q):
     comp = klb.LstmProjectedStreams(I, R, device=rank, max_frames=T)
     comp.InitData("<CellDim> %d <NumStream> %d <ParamScale> 0.05" % (C, hi - lo), seed=3)
     comp.SetTrainOptions(klb.NnetTrainOptions(LR, MMT))
-    trainer = klb.parallel.StreamShardTrainer([comp])
+    # c_path: the engine's own entry point lstmp_b200_allreduce_grads_nccl on an own ncclComm_t and a side stream
+    exchange = klb.parallel.GradientExchange([comp], torch.device("cuda", rank)) if (c_path and world > 1) else None
+    trainer = klb.parallel.StreamShardTrainer([comp], exchange=exchange)
     xs, ods = _data()
     for n in range(NCHUNK):
         x = torch.from_numpy(np.ascontiguousarray(xs[n][:, lo:hi]).reshape(-1, I)).cuda()
@@ -45,13 +47,14 @@ def _run(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_stream_sharding_matches_one_gpu():
+@pytest.mark.parametrize("c_path", [False, True])
+def test_two_gpu_stream_sharding_matches_one_gpu(c_path):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, 2, 29650, q)) for r in range(2)]
+    procs = [ctx.Process(target=_run, args=(r, 2, 29650 + int(c_path), q, c_path)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in range(2))

@@ -172,6 +172,16 @@ def test_tma_stream_groups(klb, oracle_blas, groups, monkeypatch):
     assert info["fwd_tensor_core"] == 2 and info["ngroups"] == groups and info["streams_per_group"] == 64 // groups
 
 
+def test_tma_two_slot_ring(klb, oracle_blas, monkeypatch):
+    """A 2-slot operand ring (what the tightest shapes get): fewer TMA producer threads than usual, slot reuse on
+    every chunk."""
+    from parity_util import run_pair
+    monkeypatch.setenv("LSTMP_B200_TMA_SLOTS", "2")
+    _, comp, _ = run_pair(klb, oracle_blas, I=40, C=800, R=512, S=64, T=3, nchunks=2, scale=0.05, seed=91,
+                          check_record=True)
+    assert comp.engine.info()["fwd_tensor_core"] == 2
+
+
 def test_tma_loops_few_ctas(klb, oracle_mod, monkeypatch):
     """Few CTAs with many cells / columns each: multi-round elementwise loops, wide MMA N, one cluster."""
     from parity_util import run_pair

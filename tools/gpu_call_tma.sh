@@ -3,7 +3,7 @@
 #   gpurun --timeout 900 -- 'bash tools/gpu_call_tma.sh'
 set -u
 mkdir -p gpurun_out
-timeout -s KILL 400 python -m pytest tests/test_parity_gpu.py -m gpu -q --tb=short --timeout 120 -x -k "tma or cluster or tiny or cfg3_layer1 or cfg2_recipe or determinism" > gpurun_out/tma_tests.log 2>&1
+timeout -s KILL 400 python -m pytest tests/test_parity_gpu.py -m gpu -q --tb=short --timeout 120 -x -k "tma or cluster or tiny or cfg3_layer1 or cfg2_recipe or determinism or slot" > gpurun_out/tma_tests.log 2>&1
 tail -15 gpurun_out/tma_tests.log
 B="--steps 100 --warmup 10 --no-cpu-baseline --no-e2e --no-secondary"
 for cfg in ${CFGS:-2:4 2:2 1:8 1:4}; do
