@@ -367,13 +367,251 @@ def mgpu_parity_check(klb, exchange, dev, rank, world):
         return {"ok": False, "error": str(e)[:300]}
 
 
+def bench_cfg4(args):
+    """BASELINE.json configs[3] as a whole network: LstmProjectedStreams 40->800/512 + AffineTransform 512->16624 +
+    Softmax + Xent::EvalMasked, NumStream=256 sharded over 8 GPUs = 32 streams (640 frames) per GPU, T=20, fwd + bwd +
+    [all-reduce] + update of both components.  One step = Reset, LSTM Propagate, tail PropagateEval (host mask + sparse
+    posterior in), tail Backpropagate, LSTM Backpropagate, Update x2."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    S, T, I0, C, R, P = 32, 20, 40, 800, 512, 16624
+    rows = S * T
+    desc = ("configs[3]: LstmProjectedStreams 40->800/512 + AffineTransform 512->16624 + Softmax + masked xent, "
+            "NumStream=32 per GPU (256 over 8), 20-frame BPTT, fwd+bwd+update")
+    cfg = {"workload": desc, "name": "cfg4", "num_stream_per_gpu": S, "bptt_frames": T, "learn_rate": LR,
+           "momentum": MOMENTUM, "param_scale": PARAM_SCALE,
+           "parallelism": ("streams sharded over %d GPU(s), NCCL sum-allreduce of each component's gradients per Update, "
+                           "overlapped" % world) if world > 1 else "1 GPU",
+           "l2": "GPU arm: per step 42.6 MB of logits/diff + 34 MB of tail weights stream through L2; ring of 16 chunks"}
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import oracle_py, ref_py, tail_oracle
+        Layer = ref_py.RefLstm if ref_py.available() else oracle_py.Oracle
+        mod = ref_py if ref_py.available() else oracle_py
+        if not ref_py.available():
+            oracle_py.build()
+        threads = mod.use_openblas(min(os.cpu_count() or 1, 64)) or 1
+        lstm = Layer(I0, C, R, S, np.float32)
+        lstm.set_params(oracle_py.init_params(I0, C, R, PARAM_SCALE, 4321))
+        tail = tail_oracle.TailOracle(R, P, np.float32)
+        rng = np.random.RandomState(1)
+        tail.set_params(np.concatenate([(rng.randn(P * R) * 0.1), -2.0 + (rng.rand(P) - 0.5) * 2.0]).astype(np.float32))
+        x = rng.randn(rows, I0).astype(np.float32)
+        mask = (np.arange(rows) % 5 != 0).astype(np.float32)
+        post = [[(int(rng.randint(0, P)), 1.0)] for _ in range(rows)]
+
+        def step():
+            h = lstm.propagate(x)
+            tail.propagate_eval(h, mask, post)
+            d = tail.backpropagate(h, MOMENTUM).astype(np.float32)
+            lstm.backpropagate(x, d, MOMENTUM, want_in_diff=False)
+            tail.update(LR)
+            lstm.update(LR)
+        for _ in range(max(1, args.warmup)):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+        v = rows * args.steps / dt
+        kind = "reference" if ref_py.available() else "port"
+        print(json.dumps({"impl": "reference", "metric": "frames/sec LstmProjectedStreams 800-cell/512-proj BPTT", "value": v,
+                          "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": kind,
+                                           "sample": "%d full chunks; LSTM = %s, tail = numpy restatement of the upstream "
+                                                     "AffineTransform / Softmax + the reference's EvalMasked formulation"
+                                                     % (args.steps, "oracle/_ref" if kind == "reference" else "oracle port")},
+                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import kaldi_lstm_b200 as klb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no GPU visible; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lstm = klb.LstmProjectedStreams(I0, R, device=local_rank, max_frames=T)
+    lstm.InitData("<CellDim> %d <NumStream> %d <ParamScale> %g" % (C, S, PARAM_SCALE), seed=4321)
+    lstm.SetTrainOptions(klb.NnetTrainOptions(LR, MOMENTUM))
+    tail = klb.AffineSoftmaxXent(R, P, device=local_rank, max_frames=rows)
+    tail.InitData("<ParamStddev> 0.1 <BiasMean> -2.0 <BiasRange> 2.0", seed=1)
+    tail.SetTrainOptions(klb.NnetTrainOptions(LR, MOMENTUM))
+    comps = [lstm, tail]
+    exchange = klb.parallel.GradientExchange(comps, dev) if world > 1 else None
+    rng = np.random.RandomState(2 + rank)
+    nring = 16
+    X = torch.randn(nring, rows, I0, device=dev)
+    masks = [(np.arange(rows) % 5 != (k % 5)).astype(np.float32) for k in range(nring)]
+    posts = [(np.arange(rows + 1, dtype=np.int32), rng.randint(0, P, rows).astype(np.int32), np.ones(rows, np.float32))
+             for _ in range(nring)]
+    out = torch.empty(rows, R, device=dev)
+    od = torch.empty(rows, R, device=dev)
+
+    def compute(x, mask, post, flags):
+        lstm.Reset(flags)
+        lstm.PropagateFnc(x, out)
+        tail.PropagateEval(out, mask, post)
+        tail.BackpropagateFnc(out, od)
+        if exchange is not None:
+            exchange.start(1)
+        lstm.BackpropagateFnc(x, out, od, None)
+        if exchange is not None:
+            exchange.start(0)
+            exchange.finish(0)
+        lstm.Update()
+        if exchange is not None:
+            exchange.finish(1)
+        tail.Update()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def launches():
+        return lstm.engine.info()["kernel_launches"] + tail.Stats()["kernel_launches"]
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for i in range(max(3, args.warmup)):
+        compute(X[i % nring], masks[i % nring], posts[i % nring], [1 if (i + s) % 50 == 0 else 0 for s in range(S)])
+    sync_all()
+    sampler.load = True
+    l0 = launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        compute(X[i % nring], masks[i % nring], posts[i % nring], [1 if (i + s) % 50 == 0 else 0 for s in range(S)])
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    gl = launches() - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * rows * args.steps / (ms * 1e-3)
+
+    # end to end: host utterances + host targets through the device dispatcher, loss read back every step (lagged by one)
+    e2e = None
+    if not args.no_e2e:
+        prng = np.random.RandomState(777 + rank)
+        pool = []
+        for k in range(96):
+            L = int(prng.randint(300, 701))
+            pool.append(("u%d" % k, prng.randn(L, I0).astype(np.float32), prng.randint(0, P, size=L)))
+
+        def utterances():
+            k = 0
+            while True:
+                yield pool[k % len(pool)]
+                k += 1
+        disp = klb.DeviceStreamDispatcher(S, T, 5, I0, max_utt_frames=704, device=local_rank,
+                                          shift=(prng.randn(I0) * 3).astype(np.float32),
+                                          scale=(0.25 + 0.001 * np.arange(I0)).astype(np.float32))
+        disp.open(utterances())
+        xd = [torch.empty(rows, I0, device=dev) for _ in range(2)]
+        rp = np.arange(rows + 1, dtype=np.int32)
+        ones = np.ones(rows, np.float32)
+
+        def e2e_step(i):
+            feat, mask, target, flags = disp.next_chunk(feat_out=xd[i & 1])
+            compute(feat, mask, (rp, target.astype(np.int32), ones), flags.tolist())
+        for i in range(3):
+            e2e_step(i)
+        tail.Stats()
+        sync_all()
+        st0 = disp.stats()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        loss = None
+        for i in range(args.steps):
+            e2e_step(3 + i)
+            if i % 10 == 9:
+                loss = tail.Stats()["loss"]          # Report()-style D2H of the accumulated statistics (32 bytes, syncs)
+        loss = tail.Stats()["loss"]
+        s1.record()
+        sync_all()
+        st1 = disp.stats()
+        ems = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": world * rows * args.steps / (ems * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": int((st1["h2d_bytes"] - st0["h2d_bytes"]) / args.steps + 4 * (rows + 1) + 12 * rows),
+               "d2h_bytes_per_step": 3.2, "ms_per_step": ems / args.steps, "loss": loss,
+               "what": "host utterances + host targets -> DeviceStreamDispatcher -> LSTM -> fused tail (mask + CSR posterior "
+                       "H2D from pinned staging) -> backward -> update; accumulated loss statistics D2H every 10 steps"}
+        disp.close()
+
+    lstm.engine.timing_enable(True)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nprof = min(args.steps, 30)
+    a0.record()
+    for i in range(nprof):
+        compute(X[i % nring], masks[i % nring], posts[i % nring], [0] * S)
+    a1.record()
+    torch.cuda.synchronize()
+    kinds = lstm.engine.timing_read()
+    lstm.engine.timing_enable(False)
+    lstm_us = 1e3 * sum(v[0] for v in kinds.values()) / nprof
+    step_us = 1e3 * a0.elapsed_time(a1) / nprof
+    sampler.load = False
+    if rank == 0:
+        sampler.stop()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak = float(peaks.get("bf16_tflops", peaks.get("tensor_tflops", 1500.0)))
+    tail_flops = 3 * 2.0 * rows * R * P
+    tail_us = max(step_us - lstm_us, 1e-3)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "cfg4", "--impl", "reference",
+                                "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+            cpu_baseline = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:
+            cpu_baseline = {"error": str(e)[:200]}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "frames/sec LstmProjectedStreams 800-cell/512-proj BPTT", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg, "e2e": e2e, "gpu_launches": int(gl), "clocks": sampler.summary(),
+            "roofline": {"kernel": "tail: 3 tcgen05 3xTF32 GEMMs (logits, in_diff, W gradient) + fused softmax/xent",
+                         "bound": "tensor", "achieved": tail_flops / (tail_us * 1e-6) / 1e12, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": tail_flops / (tail_us * 1e-6) / 1e12 / tf_peak, "traffic": None,
+                         "note": "logical fp32 flops of the three tail GEMMs / (step time - LSTM kernel time); the 3xTF32 "
+                                 "split issues 3x that on the tensor pipe", "tail_us_per_step": tail_us,
+                         "lstm_us_per_step": lstm_us},
+            "cpu_baseline": cpu_baseline}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["xent-cfg4"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["xent-cfg4", "cfg4"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -381,6 +619,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "xent-cfg4":
         return bench_xent(args)
+    if args.workload == "cfg4":
+        return bench_cfg4(args)
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

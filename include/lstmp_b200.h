@@ -232,6 +232,46 @@ int lstmp_b200_xent_eval_masked(lstmp_b200_xent_handle_t h, const float* frame_m
 int lstmp_b200_xent_get_stats(lstmp_b200_xent_handle_t h, lstmp_b200_xent_stats_t* out, void* stream);
 int lstmp_b200_xent_reset_stats(lstmp_b200_xent_handle_t h, void* stream);
 
+/* Softmax + EvalMasked fused: `logits` are the PRE-softmax activations (the output of
+ * the last AffineTransform); one kernel reads each row once, applies Kaldi's ApplySoftMaxPerRow (subtract the row
+ * maximum, exp, scale by 1/sum) in shared memory and writes diff = frame_mask * (softmax - target); post_out (nullable)
+ * receives the soft-max outputs themselves.  diff may alias logits (in place).  Same statistics, posterior format and
+ * error behaviour as lstmp_b200_xent_eval_masked.  num_pdf * 4 bytes must fit in shared memory (<= 200 KB). */
+int lstmp_b200_xent_eval_masked_logits(lstmp_b200_xent_handle_t h, const float* frame_mask_host, const float* logits,
+                                       size_t ld_logits, int num_frames, int num_pdf, const int32_t* post_row_ptr_host,
+                                       const int32_t* post_pdf_host, const float* post_weight_host, float* post_out,
+                                       size_t ld_post, float* diff, size_t ld_diff, void* stream);
+
+/* ---- Output tail: AffineTransform input_dim -> num_pdf + Softmax + Xent::EvalMasked --
+ * One component for the last two layers of the reference network (google/nnet.proto:4-5: <AffineTransform> 16624 512,
+ * <Softmax> 16624 16624) and the objective the trainer evaluates on them
+ * (google/nnetbin/bd-nnet-train-lstm-streams.cc:215-228): with it BASELINE.json configs[3] runs end to end.
+ * Parameters / momentum / fresh gradients are flat arenas [linearity_ (num_pdf x input_dim, row-major) | bias_ (num_pdf)]
+ * (`which`: 0 params, 1 momentum-accumulated corr, 2 fresh gradients -- the one a data-parallel caller all-reduces).
+ *   propagate_eval: logits = in * W^T + b ; y = softmax(logits) ; diff = mask * (y - t) kept inside the component;
+ *                   statistics accumulate as in lstmp_b200_xent_*; post_out (nullable, device) receives y.
+ *   backpropagate:  in_diff = diff * W (nullable) ; G(W) = diff^T * in ; G(b) = column sums of diff.
+ *   update:         corr = G + momentum * corr ; param -= learn_rate * corr   ([upstream] AffineTransform::Update with
+ *                   learn-rate coefficients 1 and no L1/L2 penalty, as in the reference's nnet.proto). */
+typedef struct lstmp_b200_tail* lstmp_b200_tail_handle_t;
+int lstmp_b200_tail_create(int input_dim, int num_pdf, int max_frames, int device, lstmp_b200_tail_handle_t* out);
+int lstmp_b200_tail_destroy(lstmp_b200_tail_handle_t h);
+int lstmp_b200_tail_arena(lstmp_b200_tail_handle_t h, int which, float** dev_ptr, size_t* count);
+int lstmp_b200_tail_set_flat(lstmp_b200_tail_handle_t h, int which, const float* src, void* stream);
+int lstmp_b200_tail_get_flat(lstmp_b200_tail_handle_t h, int which, float* dst, void* stream);
+int lstmp_b200_tail_propagate_eval(lstmp_b200_tail_handle_t h, const float* in, size_t ld_in, int num_frames,
+                                   const float* frame_mask_host, const int32_t* post_row_ptr_host,
+                                   const int32_t* post_pdf_host, const float* post_weight_host, float* post_out,
+                                   size_t ld_post, void* stream);
+int lstmp_b200_tail_backpropagate(lstmp_b200_tail_handle_t h, const float* in, size_t ld_in, float* in_diff, size_t ld_id,
+                                  int num_frames, void* stream);
+int lstmp_b200_tail_update(lstmp_b200_tail_handle_t h, float learn_rate, float momentum, void* stream);
+int lstmp_b200_tail_allreduce_grads_nccl(lstmp_b200_tail_handle_t h, void* nccl_comm, void* stream);
+/* test / debug: the diff of the last propagate_eval, [num_frames x num_pdf] to a host or device buffer */
+int lstmp_b200_tail_get_diff(lstmp_b200_tail_handle_t h, float* dst, size_t ld_dst, void* stream);
+int lstmp_b200_tail_get_stats(lstmp_b200_tail_handle_t h, lstmp_b200_xent_stats_t* out, void* stream);
+int lstmp_b200_tail_reset_stats(lstmp_b200_tail_handle_t h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

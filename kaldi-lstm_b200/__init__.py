@@ -14,4 +14,5 @@ from .engine import Engine, EngineError, XentEngine, lib_path, load_library  # n
 from .component import LstmProjectedStreams, NnetTrainOptions, TimeShift  # noqa: F401
 from .dispatch import DeviceStreamDispatcher, StreamDispatcher  # noqa: F401
 from .loss import Xent, posterior_to_csr  # noqa: F401
+from .tail import AffineSoftmaxXent, TailEngine  # noqa: F401
 from . import nnet_io, parallel  # noqa: F401

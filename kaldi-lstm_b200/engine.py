@@ -20,6 +20,11 @@ ABI_SYMBOLS = [
     "lstmp_b200_update_clipped", "lstmp_b200_time_shift",
     "lstmp_b200_dispatch_create", "lstmp_b200_dispatch_destroy", "lstmp_b200_dispatch_set_transform",
     "lstmp_b200_dispatch_load_utt", "lstmp_b200_dispatch_assemble", "lstmp_b200_dispatch_get_stats",
+    "lstmp_b200_xent_eval_masked_logits",
+    "lstmp_b200_tail_create", "lstmp_b200_tail_destroy", "lstmp_b200_tail_arena", "lstmp_b200_tail_set_flat",
+    "lstmp_b200_tail_get_flat", "lstmp_b200_tail_propagate_eval", "lstmp_b200_tail_backpropagate",
+    "lstmp_b200_tail_update", "lstmp_b200_tail_allreduce_grads_nccl", "lstmp_b200_tail_get_diff",
+    "lstmp_b200_tail_get_stats", "lstmp_b200_tail_reset_stats",
 ]
 
 TIMING_KINDS = ["input_gemm", "fwd_recurrent", "bwd_recurrent", "in_diff_gemm", "wgrad_gemms", "small_grads",

@@ -60,21 +60,26 @@ class B200StreamDispatch {
         continue;
       }
       while (!feature_reader->Done()) {                    // :153
-        keys_[s] = feature_reader->Key();
-        feats_[s] = feature_reader->Value();
-        if (!target_reader->HasKey(keys_[s])) {            // :156
-          KALDI_WARN << keys_[s] << ", missing targets";
+        // One deliberate difference: the reference assigns feats[s] / targets[s] BEFORE the two checks (:154-162), so
+        // a skipped utterance at the end of the data leaves an exhausted stream padding from the wrong matrix
+        // (possibly out of range).  Here a stream keeps its own utterance until it accepts a new one; the rows
+        // concerned are padding (mask 0, no gradient).
+        const std::string key = feature_reader->Key();
+        if (!target_reader->HasKey(key)) {                 // :156
+          KALDI_WARN << key << ", missing targets";
           num_no_tgt_mat_++;
           feature_reader->Next();
           continue;
         }
-        targets_[s] = target_reader->Value(keys_[s]);
-        if (feats_[s].NumRows() != static_cast<int32>(targets_[s].size())) {   // :163
-          KALDI_WARN << keys_[s] << ", length miss-match between feats and targets, skip";
+        if (feature_reader->Value().NumRows() != static_cast<int32>(target_reader->Value(key).size())) {   // :163
+          KALDI_WARN << key << ", length miss-match between feats and targets, skip";
           num_other_error_++;
           feature_reader->Next();
           continue;
         }
+        keys_[s] = key;
+        feats_[s] = feature_reader->Value();
+        targets_[s] = target_reader->Value(key);
         curt_[s] = 0;                                      // :168
         lent_[s] = feats_[s].NumRows();
         new_utt_flags_[s] = 1;                             // :170

@@ -28,6 +28,7 @@ class Xent:
     def __init__(self, max_frames=0, device=0):
         self._device = device
         self._engine = XentEngine(max_frames, device) if max_frames > 0 else None
+        self._carried = {"loss": 0.0, "entropy": 0.0, "correct": 0, "frames": 0, "kernel_launches": 0}
 
     def EvalMasked(self, frame_mask_host, net_out, post, diff=None):
         """diff = frame_mask * (net_out - target); accumulates loss / entropy / correct / frames on the device.
@@ -36,8 +37,11 @@ class Xent:
         rows = net_out.shape[0]
         assert rows == (len(post[0]) - 1 if isinstance(post, tuple) else len(post))     # KALDI_ASSERT nnet-loss.cc:80
         if self._engine is None or self._engine.max_frames < rows:
-            old = self._engine.stats() if self._engine is not None else None
-            assert old is None or old["frames"] == 0, "Xent created for fewer frames than this call needs"
+            if self._engine is not None:      # keep the statistics across the re-creation (as B200Xent does in C++)
+                old = self._engine.stats()
+                for k in self._carried:
+                    self._carried[k] += old[k]
+                self._engine.close()
             self._engine = XentEngine(rows, self._device)
         row_ptr, pdf, weight = post if isinstance(post, tuple) else posterior_to_csr(post)
         if diff is None:
@@ -51,8 +55,11 @@ class Xent:
         return diff
 
     def Stats(self):
-        return self._engine.stats() if self._engine is not None else {"loss": 0.0, "entropy": 0.0, "correct": 0,
-                                                                       "frames": 0, "kernel_launches": 0}
+        s = dict(self._carried)
+        if self._engine is not None:
+            for k, v in self._engine.stats().items():
+                s[k] += v
+        return s
 
     def Report(self):
         """Xent::Report, nnet-loss.cc:293-307 (without the progress vector)."""

@@ -52,11 +52,14 @@ static std::vector<Chunk> reference_loop(const std::vector<Utt>& utts, const Tgt
     for (int s = 0; s < S; s++) {
       if (curt[s] < lent[s]) { flags[s] = 0; continue; }
       while (!fr.Done()) {
+        // (the reference assigns feats[s] / targets[s] BEFORE the two checks, :154-162, so a skipped utterance at the
+        // end of the data leaves an exhausted stream padding from the WRONG matrix, possibly out of range; the padded
+        // rows are masked and carry no gradient.  Here a stream keeps its own utterance until it accepts a new one.)
         keys[s] = fr.Key();
-        feats[s] = fr.Value();
         if (!tr.HasKey(keys[s])) { fr.Next(); continue; }
+        if (fr.Value().NumRows() != (int)tr.Value(keys[s]).size()) { fr.Next(); continue; }
+        feats[s] = fr.Value();
         targets[s] = tr.Value(keys[s]);
-        if (feats[s].NumRows() != (int)targets[s].size()) { fr.Next(); continue; }
         curt[s] = 0; lent[s] = feats[s].NumRows(); flags[s] = 1;
         fr.Next();
         break;
