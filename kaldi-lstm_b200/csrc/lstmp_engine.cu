@@ -78,6 +78,7 @@ struct lstmp_b200_engine {
   bool have_bwd = false; // a backpropagate record exists for T_last
   unsigned long long launches = 0;
   int gemm_backend = 0;
+  HlWorkspace hlws;
   long long* dbg_stamps = nullptr;
   // weights-streamed mode: slices do not fit in shared memory -> per-step GEMMs + elementwise kernels
   bool streamed = false;
@@ -174,6 +175,7 @@ extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
   for (float* b : bufs)
     if (b) cudaFree(b);
   if (h->bar) cudaFree(h->bar);
+  gemm_hl_free(&h->hlws);
   if (h->rhl) cudaFree(h->rhl);  // one allocation holds rhl | mhl | dghl | drhl
   for (auto& e : h->events) {  // timing enabled but never read back
     cudaEventDestroy(e.a);
@@ -359,7 +361,9 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
   h->workspace_bytes = ws;
   h->gemm_backend = 0;
 #ifdef LSTMP_HAVE_TC_GEMM
-  h->gemm_backend = env_int("LSTMP_B200_GEMM", 1) ? 1 : 0;
+  // 2 (default): bf16 hi/lo tile images + bulk copies (lstmp_gemm_hl.cu); 1: 3xTF32 with loader warps; 0: FP32 SIMT
+  h->gemm_backend = env_int("LSTMP_B200_GEMM", 2);
+  if (h->gemm_backend < 0 || h->gemm_backend > 2) h->gemm_backend = 2;
 #endif
   if (h->d.dbg & 12) {
     if (cudaMalloc((void**)&h->dbg_stamps, (2 + 2 * 1024) * sizeof(long long)) == cudaSuccess)
@@ -521,10 +525,18 @@ extern "C" int lstmp_b200_reset(lstmp_b200_handle_t h, const int32_t* flags, int
 
 static int gemm(lstmp_b200_handle_t h, int kind, float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
                 long long lda, int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
-                cudaStream_t st) {
+                cudaStream_t st, bool reuse_a = false) {
   Timed tm(h, kind, st);
 #ifdef LSTMP_HAVE_TC_GEMM
-  if (h->gemm_backend == 1) {
+  if (h->gemm_backend == 2) {
+    bool handled = false;
+    int nl = 0;
+    CUDA_TRY(launch_gemm_hl(&h->hlws, C, ldc, M, N, K, alpha, A, lda, tA, B, ldb, tB, beta, bias, st, &handled, h->gemm_ws,
+                            h->gemm_ws_floats, &nl, reuse_a));
+    h->launches += nl;
+    if (handled) return 0;
+  }
+  if (h->gemm_backend >= 1) {
     bool handled = false;
     int nl = 1;
     CUDA_TRY(launch_gemm_tc(C, ldc, M, N, K, alpha, A, lda, tA, B, ldb, tB, beta, bias, st, &handled, h->gemm_ws,
@@ -782,7 +794,7 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
     return rc;
   // G(w_gifo_r) = DGIFO[1..T]^T * R[0..T-1]                                  (LPS.h:471)
   if ((rc = gemm(h, 4, h->grads + h->off_wr, R, 4 * C, R, num_rows, 1.f, h->dgifo, 4 * C, 1, h->rbuf, R, 0, 0.f,
-                 nullptr, st)))
+                 nullptr, st, /*reuse_a: DGIFO^T was split for the previous GEMM*/ true)))
     return rc;
   // G(w_r_m) = DR[1..T]^T * M[1..T]                                          (LPS.h:486)
   if ((rc = gemm(h, 4, h->grads + h->off_wm, C, R, C, num_rows, 1.f, h->dr, R, 1, h->mbuf, C, 0, 0.f, nullptr, st)))
@@ -935,6 +947,18 @@ extern "C" int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, i
     CUDA_TRY(launch_gemm_tc(C, (long long)ldc, M, N, K, alpha, A, (long long)lda, tA, B, (long long)ldb, tB, beta, bias,
                             st, &handled, dbg_ws, dbg_ws ? dbg_ws_floats : 0, &handled_n));
     if (!handled) return fail(LSTMP_B200_EUNSUPPORTED, "tcgen05 GEMM does not handle this shape/alignment");
+    return 0;
+  }
+  if (backend == 2) {
+    bool handled = false;
+    int nl = 0;
+    static HlWorkspace dbg_hl;          // test hook only
+    static float* dbg_ws2 = nullptr;
+    const size_t dbg_ws_floats = (size_t)4 << 20;
+    if (!dbg_ws2 && cudaMalloc((void**)&dbg_ws2, dbg_ws_floats * sizeof(float)) != cudaSuccess) dbg_ws2 = nullptr;
+    CUDA_TRY(launch_gemm_hl(&dbg_hl, C, (long long)ldc, M, N, K, alpha, A, (long long)lda, tA, B, (long long)ldb, tB, beta,
+                            bias, st, &handled, dbg_ws2, dbg_ws2 ? dbg_ws_floats : 0, &nl, false));
+    if (!handled) return fail(LSTMP_B200_EUNSUPPORTED, "bf16 hi/lo GEMM does not handle this alignment");
     return 0;
   }
 #endif

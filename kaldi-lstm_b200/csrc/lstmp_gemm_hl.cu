@@ -1,0 +1,366 @@
+// tcgen05 GEMM fed by bulk copies of PRE-SPLIT operands, sm_100a only.
+//
+//   C[M x N] = alpha * op(A) * op(B) + beta * C (+ bias[n])       fp32 in, fp32 out
+//
+// Same call sites as lstmp_gemm_tc.cu (the contractions outside the time loop, LPS.h:246, :457, :468, :471, :486, and
+// the three GEMMs of the output tail) and the same FP32-faithful idea as the TMA-fed time loops: every fp32 operand x is
+// split once into two bf16 pieces, hi = bf16(x) and lo = bf16(x - hi), and the product is accumulated in FP32 in TMEM as
+// hi*hi + hi*lo + lo*hi + lo*lo with tcgen05.mma.kind::f16 (K = 16 per instruction: half the instructions of the
+// 3xTF32 kernel for the same K).  What changes is WHERE the split happens:
+//
+//   1. split_hl_kernel (one elementwise pass per operand, HBM-bound) writes the operand as "tile images": for every
+//      [128 rows x 64 k] tile the ready-made SWIZZLE_128B K-major shared-memory image of its hi half and of its lo
+//      half (16 KB each), zero-padded to whole tiles; an operand stored with the contraction index as the ROW index
+//      (m/n-contiguous, e.g. DGIFO^T for the weight gradients) is transposed on the way.
+//   2. gemm_hl_kernel: one thread issues four 16 KB cp.async.bulk copies per 64-deep K block straight into the UMMA
+//      ring (mbarrier expect_tx), one warp issues 16 MMAs per block, four warps run the epilogue.  No loader warps, no
+//      register pass, no generic-proxy stores into operand tiles, no bounds logic on the operand side.
+//
+// (lstmp_gemm_tc.cu moves 32 KB in, 32 KB back out and 64 KB of hi/lo tiles through shared memory per 32-deep K block
+// with eight loader warps and reaches ~1.9 k cycles per block against 0.78 k of MMA time)
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "lstmp_common.cuh"
+#include "lstmp_kernels.h"
+#include "lstmp_tc.cuh"
+
+namespace lstmp {
+namespace hl {
+constexpr int BM = 128, BN = 128, BK = 64;           // tile: 128 x 128 outputs, 64 k per stage
+constexpr uint32_t TILE = 128 * 128;                 // bytes of one [128 rows x 64 k] bf16 image (hi or lo)
+constexpr int NSTAGE = 3;                            // stages of A_hi | A_lo | B_hi | B_lo = 64 KB
+constexpr uint32_t STAGE = 4 * TILE;
+constexpr int THREADS = 192;                         // warp 0 producer, warp 1 MMA issuer + TMEM, warps 2-5 epilogue
+constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 + 256;
+
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Operand [R x K] (R = M or N) -> images img[(rt * nkt + kt) * 2 + {hi, lo}][TILE], rt = r / 128, kt = k / 64.
+// TRANSPOSED == false: element (r, k) at src[r * ld + k]; true: at src[k * ld + r].
+// One thread per 16-byte unit (8 consecutive k of one row); whole tiles are written (zeros outside R x K).
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256) split_hl_kernel(uint8_t* __restrict__ img, const float* __restrict__ src,
+                                                       long long ld, int R, int K, int nrt, int nkt) {
+  const long long units = (long long)nrt * nkt * 128 * 8;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units;
+       u += (long long)gridDim.x * blockDim.x) {
+    int rl, kc, kt, rt;
+    if (!TRANSPOSED) {  // consecutive threads: consecutive k units of a row (coalesced reads along k)
+      kc = (int)(u & 7);
+      long long t = u >> 3;
+      kt = (int)(t % nkt);
+      t /= nkt;
+      rl = (int)(t & 127);
+      rt = (int)(t >> 7);
+    } else {            // consecutive threads: consecutive rows (= consecutive source columns: coalesced reads)
+      rl = (int)(u & 127);
+      long long t = u >> 7;
+      rt = (int)(t % nrt);
+      t /= nrt;
+      kc = (int)(t & 7);
+      kt = (int)(t >> 3);
+    }
+    const int r = rt * 128 + rl, k0 = kt * BK + kc * 8;
+    float v[8];
+    if (!TRANSPOSED) {
+      if (r < R && k0 + 7 < K && ((ld & 3) == 0)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + (long long)r * ld + k0));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src + (long long)r * ld + k0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (r < R && k0 + q < K) ? __ldg(src + (long long)r * ld + k0 + q) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = (r < R && k0 + q < K) ? __ldg(src + (long long)(k0 + q) * ld + r) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    uint8_t* t = img + ((size_t)rt * nkt + kt) * 2 * TILE + tc::sw128_off(rl, kc);
+    *reinterpret_cast<uint4*>(t) = hi;
+    *reinterpret_cast<uint4*>(t + TILE) = lo;
+  }
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+// grid = (N tiles, M tiles, K splits).  a_img / b_img: tile images of op(A) [M x K] and op(B)^T [N x K].
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_hl_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int nkt, float alpha, const uint8_t* __restrict__ a_img,
+               const uint8_t* __restrict__ b_img, float beta, const float* __restrict__ bias, int kt_per_split,
+               float* __restrict__ split_ws) {
+  extern __shared__ __align__(128) uint8_t smem_raw_hl[];
+  uint8_t* tiles = smem_raw_hl + ((1024u - (smem_u32(smem_raw_hl) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * STAGE);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* accum_ready = empty + NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  int kt0 = 0, nk = nkt;
+  if (split_ws) {  // split-K: raw partial sums to split_ws[z][M x N]; splitk_reduce applies alpha / beta / bias
+    kt0 = blockIdx.z * kt_per_split;
+    nk = min(kt_per_split, nkt - kt0);
+    Cm = split_ws + (size_t)blockIdx.z * M * N;
+    ldc = N;
+    alpha = 1.f;
+    beta = 0.f;
+    bias = nullptr;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t tiles_s = smem_u32(tiles);
+
+  if (warp == 0) {
+    // ------------------------------ producer: 4 bulk copies per K block ----------------------
+    if (lane == 0) {
+      const uint8_t* ap = a_img + ((size_t)blockIdx.y * nkt + kt0) * 2 * TILE;   // A_hi | A_lo of (mt, kt) are adjacent
+      const uint8_t* bp = b_img + ((size_t)blockIdx.x * nkt + kt0) * 2 * TILE;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % NSTAGE;
+        if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
+        mbar_arrive_expect_tx(&full[s], STAGE);
+        const uint32_t dst = tiles_s + s * STAGE;
+        bulk_g2s(dst, ap + (size_t)kb * 2 * TILE, 2 * TILE, &full[s]);
+        bulk_g2s(dst + 2 * TILE, bp + (size_t)kb * 2 * TILE, 2 * TILE, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer -----------------------------------------------
+    // kind::f16, bf16 x bf16 -> fp32, both operands K-major: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % NSTAGE;
+      mbar_wait(&full[s], (uint32_t)((kb / NSTAGE) & 1));
+      tc::tc_fence_after();
+      {
+        const uint32_t a_hi = tiles_s + s * STAGE, a_lo = a_hi + TILE, b_hi = a_hi + 2 * TILE, b_lo = b_hi + TILE;
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j) {
+          const uint64_t dah = tc::make_desc_sw128(a_hi + 32 * j), dal = tc::make_desc_sw128(a_lo + 32 * j);
+          const uint64_t dbh = tc::make_desc_sw128(b_hi + 32 * j), dbl = tc::make_desc_sw128(b_lo + 32 * j);
+          if (tc::elect_one()) mma_bf16(tmem_base, dal, dbl, idesc, (kb | j) ? 1u : 0u);  // small terms first
+          if (tc::elect_one()) mma_bf16(tmem_base, dal, dbh, idesc, 1u);
+          if (tc::elect_one()) mma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          if (tc::elect_one()) mma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        }
+        if (tc::elect_one()) {
+          tc::umma_commit(&empty[s]);
+          if (kb == nk - 1) tc::umma_commit(accum_ready);
+        }
+      }
+      __syncwarp();
+    }
+    tc::tc_fence_before();
+  } else {
+    // ------------------------------ epilogue (warps 2-5: TMEM lane quadrants 2, 3, 0, 1) -----
+    if (nk > 0) {
+      mbar_wait(accum_ready, 0);
+      tc::tc_fence_after();
+    }
+    const int quad = warp & 3;
+    const int gm = m0 + quad * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      if (nk > 0) {
+        tc::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = 0.f;
+      }
+      if (gm < M) {
+        float* crow = Cm + (size_t)gm * ldc;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int gn = n0 + c + j;
+          if (gn + 3 < N && ((ldc & 3) == 0)) {
+            float4 o = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+            if (beta != 0.f) {
+              const float4 cc = *reinterpret_cast<const float4*>(crow + gn);
+              o.x += beta * cc.x; o.y += beta * cc.y; o.z += beta * cc.z; o.w += beta * cc.w;
+            }
+            if (bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + gn));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(crow + gn) = o;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (gn + q < N) {
+                float o = alpha * v[j + q];
+                if (beta != 0.f) o += beta * crow[gn + q];
+                if (bias) o += bias[gn + q];
+                crow[gn + q] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+}  // namespace hl
+
+cudaError_t launch_splitk_reduce(float* C, long long ldc, int M, int N, float alpha, float beta, const float* bias,
+                                 const float* ws, int splits, cudaStream_t stream);  // lstmp_gemm_tc.cu
+
+size_t gemm_hl_image_bytes(int rows, int K) {
+  return (size_t)((rows + 127) / 128) * ((K + hl::BK - 1) / hl::BK) * 2 * hl::TILE;
+}
+
+// src: the operand as stored; rows x K is its logical [R x K] shape; transposed: element (r, k) at src[k * ld + r].
+cudaError_t gemm_hl_split(uint8_t* img, const float* src, long long ld, int rows, int K, bool transposed,
+                          cudaStream_t stream) {
+  const int nrt = (rows + 127) / 128, nkt = (K + hl::BK - 1) / hl::BK;
+  const long long units = (long long)nrt * nkt * 128 * 8;
+  int blocks = (int)((units + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (transposed) hl::split_hl_kernel<true><<<blocks, 256, 0, stream>>>(img, src, ld, rows, K, nrt, nkt);
+  else hl::split_hl_kernel<false><<<blocks, 256, 0, stream>>>(img, src, ld, rows, K, nrt, nkt);
+  return cudaGetLastError();
+}
+
+cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alpha, const uint8_t* a_img,
+                        const uint8_t* b_img, float beta, const float* bias, cudaStream_t stream, float* ws,
+                        size_t ws_floats, int* nlaunch) {
+  *nlaunch = 1;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!attr_set[dev & 63]) {
+    e = cudaFuncSetAttribute((const void*)hl::gemm_hl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hl::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  const int nkt = (K + hl::BK - 1) / hl::BK;
+  dim3 grid((N + hl::BN - 1) / hl::BN, (M + hl::BM - 1) / hl::BM), block(hl::THREADS);
+  const int tiles = grid.x * grid.y;
+  int splits = 1;
+  // split-K when the output tiles alone cannot fill the 148 SMs (in_diff: 40 tiles, G(w_r_m): 28 tiles)
+  if (ws && tiles < 100 && nkt >= 4 && (N & 3) == 0) {
+    splits = 148 / tiles;
+    if (splits > 8) splits = 8;
+    if (splits > nkt / 2) splits = nkt / 2;
+    while (splits > 1 && (size_t)splits * M * N > ws_floats) --splits;
+  }
+  if (splits > 1) {
+    const int kts = (nkt + splits - 1) / splits;
+    splits = (nkt + kts - 1) / kts;
+    grid.z = splits;
+    hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(C, ldc, M, N, nkt, alpha, a_img, b_img, beta, bias, kts, ws);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    *nlaunch = 2;
+    return launch_splitk_reduce(C, ldc, M, N, alpha, beta, bias, ws, splits, stream);
+  }
+  hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(C, ldc, M, N, nkt, alpha, a_img, b_img, beta, bias, nkt, nullptr);
+  return cudaGetLastError();
+}
+
+
+// One call = split both operands (unless the caller says op(A)'s image of the previous call is still valid), run the
+// GEMM.  The image buffers grow on demand and belong to the caller's handle (one stream at a time per handle).
+cudaError_t launch_gemm_hl(HlWorkspace* w, float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
+                           long long lda, int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
+                           cudaStream_t stream, bool* handled, float* ws, size_t ws_floats, int* nlaunch, bool reuse_a) {
+  *handled = false;
+  *nlaunch = 0;
+  if (!w || M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(C) || (bias && !al16(bias)) || !al16(A) || !al16(B)) return cudaSuccess;
+  const size_t na = gemm_hl_image_bytes(M, K), nb = gemm_hl_image_bytes(N, K);
+  auto grow = [&](uint8_t** p, size_t* cap, size_t need) -> cudaError_t {
+    if (need <= *cap) return cudaSuccess;
+    if (*p) {
+      cudaError_t e = cudaFree(*p);  // (waits for the device: earlier kernels may still read the old buffer)
+      if (e != cudaSuccess) return e;
+      *p = nullptr;
+      *cap = 0;
+    }
+    cudaError_t e = cudaMalloc((void**)p, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+  };
+  if (!(reuse_a && w->a && w->a_bytes == na)) {
+    cudaError_t e = grow(&w->a, &w->a_cap, na);
+    if (e != cudaSuccess) return e;
+    e = gemm_hl_split(w->a, A, lda, M, K, tA != 0, stream);
+    if (e != cudaSuccess) return e;
+    w->a_bytes = na;
+    ++*nlaunch;
+  }
+  cudaError_t e = grow(&w->b, &w->b_cap, nb);
+  if (e != cudaSuccess) return e;
+  e = gemm_hl_split(w->b, B, ldb, N, K, tB == 0, stream);
+  if (e != cudaSuccess) return e;
+  ++*nlaunch;
+  int nl = 0;
+  e = gemm_hl_run(C, ldc, M, N, K, alpha, w->a, w->b, beta, bias, stream, ws, ws_floats, &nl);
+  *nlaunch += nl;
+  *handled = true;
+  return e;
+}
+
+void gemm_hl_free(HlWorkspace* w) {
+  if (!w) return;
+  if (w->a) cudaFree(w->a);
+  if (w->b) cudaFree(w->b);
+  w->a = w->b = nullptr;
+  w->a_cap = w->b_cap = w->a_bytes = 0;
+}
+
+}  // namespace lstmp

@@ -505,6 +505,15 @@ static cudaError_t launch_one(float* C, long long ldc, int M, int N, int K, floa
 }
 }  // namespace tc
 
+cudaError_t launch_splitk_reduce(float* C, long long ldc, int M, int N, float alpha, float beta, const float* bias,
+                                 const float* ws, int splits, cudaStream_t stream) {
+  int rb = (int)(((long long)M * (N >> 2) + 255) / 256);
+  if (rb > 148 * 4) rb = 148 * 4;
+  if (rb < 1) rb = 1;
+  tc::splitk_reduce_kernel<<<rb, 256, 0, stream>>>(C, ldc, M, N, alpha, beta, bias, ws, splits);
+  return cudaGetLastError();
+}
+
 // tA/tB as in launch_gemm: op(A) is M x K.  tA == 0: A stored [M x K] (k contiguous -> K-major);
 // tA == 1: A stored [K x M] (m contiguous -> MN-major).  op(B) is K x N.  tB == 0: B stored [K x N]
 // (n contiguous -> MN-major); tB == 1: B stored [N x K] (k contiguous -> K-major).

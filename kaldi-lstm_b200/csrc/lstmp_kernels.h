@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 
 namespace lstmp {
 
@@ -154,6 +155,16 @@ inline int fwd_tma_barriers(int T) { return 2 * T; }
 cudaError_t launch_gemm(float* C, long long ldc, int M, int N, int K, float alpha, const float* A, long long lda,
                         int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
                         cudaStream_t stream);
+
+// tcgen05 GEMM on pre-split bf16 hi/lo tile images fed by bulk copies (lstmp_gemm_hl.cu); same contract as launch_gemm.
+struct HlWorkspace {
+  uint8_t *a = nullptr, *b = nullptr;   // tile images of op(A) [M x K] and op(B)^T [N x K]
+  size_t a_cap = 0, b_cap = 0, a_bytes = 0;
+};
+cudaError_t launch_gemm_hl(HlWorkspace* w, float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
+                           long long lda, int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
+                           cudaStream_t stream, bool* handled, float* ws, size_t ws_floats, int* nlaunch, bool reuse_a);
+void gemm_hl_free(HlWorkspace* w);
 
 // corr = G + momentum*corr ; param -= lr*corr   over the flat arena
 // clip > 0: corr is clamped element-wise to [-clip, clip] before the step (the standard/ component's gradient clip)

@@ -970,7 +970,11 @@ cudaError_t launch_bwd_tma(const BwdTmaParams& p, size_t smem_bytes, cudaStream_
   // co-residency of the whole grid is what the grid barrier needs: the grid was sized with
   // cudaOccupancyMaxActiveClusters; the cooperative attribute makes the driver check it too.  Drivers that refuse
   // cluster + cooperative in one launch get the plain cluster launch (same co-residency by construction).
-  static int coop_ok = 1;
+  // LSTMP_B200_BWD_COOP=0 skips the cooperative attribute (Nsight Compute cannot replay a cooperative cluster launch)
+  static int coop_ok = [] {
+    const char* v = getenv("LSTMP_B200_BWD_COOP");
+    return (v && *v) ? atoi(v) : 1;
+  }();
   if (coop_ok) {
     cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, lstmp_bwd_tma_kernel, p);

@@ -21,6 +21,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -85,6 +86,8 @@ struct lstmp_b200_tail {
   float* gemm_ws = nullptr;
   size_t gemm_ws_floats = 0;
   lstmp_b200_xent_handle_t xent = nullptr;
+  HlWorkspace hlws;
+  int gemm_backend = 2;
   int rows_last = 0;
   unsigned long long launches = 0;
 };
@@ -94,6 +97,12 @@ static int tail_gemm(lstmp_b200_tail* h, float* C, long long ldc, int M, int N, 
 #ifdef LSTMP_HAVE_TC_GEMM
   bool handled = false;
   int nl = 1;
+  if (h->gemm_backend == 2) {
+    T_TRY(launch_gemm_hl(&h->hlws, C, ldc, M, N, K, 1.f, A, lda, tA, B, ldb, tB, 0.f, bias, st, &handled, h->gemm_ws,
+                         h->gemm_ws_floats, &nl, false));
+    h->launches += nl;
+    if (handled) return 0;
+  }
   T_TRY(launch_gemm_tc(C, ldc, M, N, K, 1.f, A, lda, tA, B, ldb, tB, 0.f, bias, st, &handled, h->gemm_ws,
                        h->gemm_ws_floats, &nl));
   if (handled) {
@@ -114,6 +123,7 @@ extern "C" int lstmp_b200_tail_destroy(lstmp_b200_tail_handle_t h) {
   for (float* b : bufs)
     if (b) cudaFree(b);
   lstmp_b200_xent_destroy(h->xent);
+  gemm_hl_free(&h->hlws);
   delete h;
   return 0;
 }
@@ -139,6 +149,10 @@ extern "C" int lstmp_b200_tail_create(int input_dim, int num_pdf, int max_frames
   h->I = input_dim; h->P = num_pdf; h->max_rows = max_frames; h->device = device;
   h->nparams = (size_t)num_pdf * input_dim + num_pdf;
   h->gemm_ws_floats = (size_t)4 << 20;
+  {
+    const char* v = getenv("LSTMP_B200_GEMM");
+    if (v && *v) h->gemm_backend = atoi(v);
+  }
   bool ok = cudaMalloc((void**)&h->params, h->nparams * sizeof(float)) == cudaSuccess &&
             cudaMalloc((void**)&h->corr, h->nparams * sizeof(float)) == cudaSuccess &&
             cudaMalloc((void**)&h->grads, h->nparams * sizeof(float)) == cudaSuccess &&

@@ -69,3 +69,18 @@ def test_gemm_tcgen05_3xtf32(eng, shape):
 def test_gemm_tcgen05_pitched(eng):
     assert _case(eng, 1, 1280, 512, 3200, 0, 0, pad=12) <= 5e-5
     assert _case(eng, 1, 3200, 512, 1280, 1, 0, pad=8) <= 5e-5
+
+
+# ---- bf16 hi/lo tile-image GEMM (lstmp_gemm_hl.cu): pre-split operands + bulk copies + tcgen05 kind::f16 -----------
+@pytest.mark.parametrize("shape", SHAPES + [(640, 16624, 512, 0, 1), (640, 512, 16624, 0, 0), (16624, 512, 640, 1, 0)])
+def test_gemm_hl_bf16_split(eng, shape):
+    M, N, K, tA, tB = shape
+    err = _case(eng, 2, M, N, K, tA, tB, alpha=0.7, beta=0.3, bias=True)
+    assert err <= 2e-5, "bf16 hi/lo (4-term) error %.3e (single-pass bf16 would be ~4e-3)" % err
+
+
+def test_gemm_hl_pitched_and_alpha_beta(eng):
+    assert _case(eng, 2, 1280, 512, 3200, 0, 0, pad=12) <= 2e-5
+    assert _case(eng, 2, 3200, 512, 1280, 1, 0, pad=8) <= 2e-5
+    assert _case(eng, 2, 1280, 3200, 512, 0, 1, alpha=1.0, beta=0.0, bias=False) <= 2e-5
+    assert _case(eng, 2, 256, 384, 200, 0, 0, alpha=-1.5, beta=1.0, bias=False, seed=3) <= 2e-5

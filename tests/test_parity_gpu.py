@@ -215,6 +215,69 @@ def test_cfg5_shape_2048_1024(klb, oracle_blas):
     assert comp.engine.info()["weights_streamed"] == 1
 
 
+def test_cfg5_full_shape_s64_t20(klb, oracle_blas):
+    """BASELINE.json configs[4] at the per-GPU shape the config names: 40-in, 2048-cell, 1024-proj, NumStream=64, 20-frame
+    BPTT (weights-streamed mode), one chunk with momentum against the oracle (about 85 GFLOP on the host)."""
+    from parity_util import run_pair
+    _, comp, _ = run_pair(klb, oracle_blas, I=40, C=2048, R=1024, S=64, T=20, nchunks=1, scale=0.02, seed=33,
+                          resets=[(np.arange(64) % 4 == 1).astype(np.int32)])
+    assert comp.engine.info()["weights_streamed"] == 1
+
+
+def test_cfg3_stacked_two_layers(klb, oracle_blas):
+    """BASELINE.json configs[2] as the STACK the benchmark times (bench.py compute()): 40->800/512->800/512, NumStream=64,
+    T=20, two chunks with carried state and a Reset on a subset of streams; layer 2's in_diff is layer 1's out_diff.
+    Both layers against two chained oracles: top output, bottom in_diff path (layer-1 gradients), parameters after
+    Update of both layers."""
+    import torch
+    from parity_util import assert_close
+    S, T, lr, mmt = 64, 20, 1e-3, 0.9
+    shapes = [(40, 800, 512), (512, 800, 512)]
+    layers, oracles = [], []
+    for li, (I, C, R) in enumerate(shapes):
+        flat = oracle_blas.init_params(I, C, R, 0.05, 200 + li)
+        c = klb.LstmProjectedStreams(I, R, max_frames=T)
+        c.InitData("<CellDim> %d <NumStream> %d" % (C, S))
+        c.SetParams(flat)
+        c.SetTrainOptions(klb.NnetTrainOptions(lr, mmt))
+        o = oracle_blas.Oracle(I, C, R, S, np.float32)
+        o.set_params(flat)
+        layers.append(c)
+        oracles.append(o)
+    rng = np.random.RandomState(17)
+    outs = [torch.empty(S * T, R, device="cuda") for (_, _, R) in shapes]
+    in_diff2 = torch.empty(S * T, 512, device="cuda")
+    for n in range(2):
+        x = rng.randn(S * T, 40).astype(np.float32)
+        od = (rng.randn(S * T, 512) * 0.1).astype(np.float32)
+        flags = ((np.arange(S) + n) % 3 == 0).astype(np.int32) if n else np.zeros(S, np.int32)
+        xd, odd = torch.from_numpy(x).cuda(), torch.from_numpy(od).cuda()
+        h = xd
+        for li, c in enumerate(layers):           # exactly bench.py compute()
+            c.Reset(list(flags))
+            c.PropagateFnc(h, outs[li])
+            h = outs[li]
+        layers[1].BackpropagateFnc(outs[0], outs[1], odd, in_diff2)
+        layers[0].BackpropagateFnc(xd, outs[0], in_diff2, None)
+        for c in layers:
+            c.Update()
+        # two chained oracles
+        for o in oracles:
+            o.reset(flags)
+        h1 = oracles[0].propagate(x)
+        h2 = oracles[1].propagate(h1)
+        d1 = oracles[1].backpropagate(h1, od, mmt, want_in_diff=True)
+        oracles[0].backpropagate(x, d1, mmt, want_in_diff=False)
+        for o in oracles:
+            o.update(lr)
+        assert_close(outs[0].cpu().numpy(), h1, "chunk %d layer-1 out" % n)
+        assert_close(outs[1].cpu().numpy(), h2, "chunk %d layer-2 out" % n)
+        assert_close(in_diff2.cpu().numpy(), d1, "chunk %d layer-2 in_diff" % n)
+        for li in range(2):
+            assert_close(layers[li].GetGradients(), oracles[li].get_grads(), "chunk %d layer-%d corr" % (n, li + 1))
+            assert_close(layers[li].GetParams(), oracles[li].get_params(), "chunk %d layer-%d params" % (n, li + 1))
+
+
 def test_growing_chunk_length(klb, oracle_mod):
     """The reference resizes its buffers per call (LPS.h:230); the mirror re-creates the engine."""
     from parity_util import run_pair
