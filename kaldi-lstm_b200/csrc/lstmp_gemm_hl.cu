@@ -199,47 +199,58 @@ gemm_hl_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int nkt, flo
     tc::tc_fence_before();
   } else {
     // ------------------------------ epilogue (warps 2-5: TMEM lane quadrants 2, 3, 0, 1) -----
+    // TMEM -> shared memory (the operand ring is idle once the last MMA has committed) -> global memory with whole
+    // rows per warp: 512 contiguous bytes per store instruction instead of 32 scattered 16-byte pieces.
+    constexpr int LDT = BN + 4;  // padded row stride (floats): conflict-free 128-bit stores of a TMEM lane's row
+    float* stage_t = reinterpret_cast<float*>(tiles);
     if (nk > 0) {
       mbar_wait(accum_ready, 0);
       tc::tc_fence_after();
     }
     const int quad = warp & 3;
-    const int gm = m0 + quad * 32 + lane;
+    {
+      float* srow = stage_t + (size_t)(quad * 32 + lane) * LDT;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      float v[16];
-      if (nk > 0) {
-        tc::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
-      } else {
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        if (nk > 0) {
+          tc::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = 0.f;
+          for (int q = 0; q < 16; ++q) v[q] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(srow + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-      if (gm < M) {
-        float* crow = Cm + (size_t)gm * ldc;
+    }
+    __syncwarp();  // each warp re-reads only the 32 rows it wrote itself
+    const int gn = n0 + 4 * lane;
+    const bool vec_ok = ((ldc & 3) == 0) && gn + 3 < N;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && vec_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + gn));
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const int gm = m0 + quad * 32 + rr;
+      if (gm >= M) break;
+      const float4 a4 = *reinterpret_cast<const float4*>(stage_t + (size_t)(quad * 32 + rr) * LDT + 4 * lane);
+      float* crow = Cm + (size_t)gm * ldc;
+      if (vec_ok) {
+        float4 o = make_float4(alpha * a4.x, alpha * a4.y, alpha * a4.z, alpha * a4.w);
+        if (beta != 0.f) {
+          const float4 cc = *reinterpret_cast<const float4*>(crow + gn);
+          o.x += beta * cc.x; o.y += beta * cc.y; o.z += beta * cc.z; o.w += beta * cc.w;
+        }
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        *reinterpret_cast<float4*>(crow + gn) = o;
+      } else {
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const int gn = n0 + c + j;
-          if (gn + 3 < N && ((ldc & 3) == 0)) {
-            float4 o = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
-            if (beta != 0.f) {
-              const float4 cc = *reinterpret_cast<const float4*>(crow + gn);
-              o.x += beta * cc.x; o.y += beta * cc.y; o.z += beta * cc.z; o.w += beta * cc.w;
-            }
-            if (bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + gn));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            *reinterpret_cast<float4*>(crow + gn) = o;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (gn + q < N) {
-                float o = alpha * v[j + q];
-                if (beta != 0.f) o += beta * crow[gn + q];
-                if (bias) o += bias[gn + q];
-                crow[gn + q] = o;
-              }
-            }
+        for (int q = 0; q < 4; ++q) {
+          if (gn + q < N) {
+            float o = alpha * av[q];
+            if (beta != 0.f) o += beta * crow[gn + q];
+            if (bias) o += bias[gn + q];
+            crow[gn + q] = o;
           }
         }
       }

@@ -684,17 +684,24 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
     stamp(43);
     // ============ phase B: d_m = d_r * W_r_m (my cells) (:408) + gate derivatives (:411-440)
     if (nc > 0) {
-      // prefetch this thread's first element's activations while d_r is gathered and contracted
-      float yg = 0.f, yi = 0.f, yf = 0.f, yo = 0.f, yc = 0.f, ycp = 0.f, yh = 0.f, yfn = 0.f;
-      if (tid < Sg * nc) {
-        int s = tid / nc, cl = tid - s * nc;
-        size_t row = (size_t)tt * S + s_base + s;
-        const float* gp = p.gifo + row * (4 * C) + c0 + cl;
-        yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
-        yc = p.cbuf[(row + S) * C + c0 + cl];
-        ycp = p.cbuf[row * C + c0 + cl];
-        yh = p.hbuf[row * C + c0 + cl];
-        yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;
+      // prefetch this thread's first TWO elements' activations while d_r is gathered and contracted (with two stream
+      // groups and 4-CTA clusters a CTA owns 13 cells x 32 streams = 416 elements: a second round for 32 threads)
+      float yv[2][8];
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        const int idx = tid + rd * kThreads;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) yv[rd][q] = 0.f;
+        if (idx < Sg * nc) {
+          int s = idx / nc, cl = idx - s * nc;
+          size_t row = (size_t)tt * S + s_base + s;
+          const float* gp = p.gifo + row * (4 * C) + c0 + cl;
+          yv[rd][0] = gp[0]; yv[rd][1] = gp[C]; yv[rd][2] = gp[2 * C]; yv[rd][3] = gp[3 * C];
+          yv[rd][4] = p.cbuf[(row + S) * C + c0 + cl];
+          yv[rd][5] = p.cbuf[row * C + c0 + cl];
+          yv[rd][6] = p.hbuf[row * C + c0 + cl];
+          yv[rd][7] = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;
+        }
       }
       tma_product(ps, rg, gs, true, drhl, Sg, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b,
                   tmem_base + COL_B, cpc, nc, red, ldred);
@@ -702,7 +709,13 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       for (int idx = tid; idx < Sg * nc; idx += kThreads) {
         int s = idx / nc, cl = idx - s * nc;
         size_t row = (size_t)tt * S + s_base + s;
-        if (idx >= kThreads) {
+        float yg, yi, yf, yo, yc, ycp, yh, yfn;
+        if (idx < 2 * kThreads) {
+          const int rd = idx >= kThreads ? 1 : 0;
+          yg = rd ? yv[1][0] : yv[0][0]; yi = rd ? yv[1][1] : yv[0][1]; yf = rd ? yv[1][2] : yv[0][2];
+          yo = rd ? yv[1][3] : yv[0][3]; yc = rd ? yv[1][4] : yv[0][4]; ycp = rd ? yv[1][5] : yv[0][5];
+          yh = rd ? yv[1][6] : yv[0][6]; yfn = rd ? yv[1][7] : yv[0][7];
+        } else {
           const float* gp = p.gifo + row * (4 * C) + c0 + cl;
           yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
           yc = p.cbuf[(row + S) * C + c0 + cl];
