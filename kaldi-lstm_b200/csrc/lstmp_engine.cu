@@ -63,10 +63,6 @@ struct lstmp_b200_engine {
   FwdParams fp{};
   BwdParams bp{};
   size_t fwd_smem = 0, bwd_smem = 0;
-  // tensor-core forward time loop (num_stream <= 64): own decomposition (one stream group) and barrier counter
-  bool fwd_tc = false;
-  FwdTcParams ftp{};
-  size_t fwd_tc_smem = 0;
   unsigned bar_base_tc = 0, bar_base_tcb = 0;
   // TMA-fed tcgen05 time loops, forward and backward (lstmp_recurrent_tma.cu)
   bool rec_tma = false;
@@ -259,8 +255,8 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
       delete h;
       return fail((int)e, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e));
     }
-    // default: TMA-fed tcgen05 loops in both directions (LSTMP_B200_REC=2); 1 = the round-1 tcgen05 forward loop with
-    // register loaders + FFMA backward; 0 = FFMA kernels
+    // default: tcgen05 loops fed by bulk copies in both directions (LSTMP_B200_REC=2); 0 = the FP32 FFMA kernels (also
+    // the fallback for num_stream > 64 per group or cell / recurrent dims that are not multiples of 8)
     const int rec = env_int("LSTMP_B200_REC", 2);
     if (rec >= 2) {
       const int kp = env_int("LSTMP_B200_BWD_KP", 4);
@@ -292,16 +288,6 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
         } else {
           cudaGetLastError();
         }
-      }
-    }
-    if (!h->rec_tma && rec >= 1 && env_int("LSTMP_B200_TC_FWD", 1) && h->d.ngroups * h->d.ctas_per_group == sm_use) {
-      FwdTcParams t{};
-      size_t sz = 0;
-      if (fwd_tc_plan(C, R, S, sm_use, smem_limit, env_int("LSTMP_B200_TC_LOADER", env_int("LSTMP_B200_TC_STAGED", 1) ? 1 : 0), &t, &sz) && fwd_tc_set_smem_limit(sz) == cudaSuccess) {
-        h->fwd_tc = true;
-        t.stagger = env_int("LSTMP_B200_TC_STAGGER", 1);
-        h->ftp = t;
-        h->fwd_tc_smem = sz;
       }
     }
   }
@@ -628,33 +614,6 @@ extern "C" int lstmp_b200_propagate(lstmp_b200_handle_t h, const float* in, size
     h->have_bwd = false;
     return 0;
   }
-  if (h->fwd_tc) {
-    FwdTcParams q = h->ftp;
-    q.I = I; q.C = C; q.R = R; q.S = S; q.T = T;
-    q.w_gifo_r = h->params + h->off_wr;
-    q.w_r_m = h->params + h->off_wm;
-    q.p_i = h->params + h->off_pi;
-    q.p_f = h->params + h->off_pf;
-    q.p_o = h->params + h->off_po;
-    q.gifo = h->gifo; q.cbuf = h->cbuf; q.hbuf = h->hbuf; q.mbuf = h->mbuf; q.rbuf = h->rbuf;
-    q.out = out;
-    q.ld_out = (long long)ld_out;
-    q.state_c = h->state_c;
-    q.state_r = h->state_r;
-    q.bar = h->bar + (size_t)kMaxGroupsHost * kBarStride;
-    q.bar_base = h->bar_base_tc;
-    q.dbg = h->d.dbg;
-    q.dbg_stamps = h->dbg_stamps;
-    {
-      Timed tm(h, 1, st);
-      CUDA_TRY(launch_fwd_tc(q, h->fwd_tc_smem, st));
-    }
-    h->launches++;
-    h->bar_base_tc += (unsigned)(fwd_barriers(T) * q.nctas);
-    h->T_last = T;
-    h->have_bwd = false;
-    return 0;
-  }
   FwdParams p = h->fp;
   p.I = I; p.C = C; p.R = R; p.S = S; p.T = T;
   p.d = h->d;
@@ -851,13 +810,13 @@ extern "C" int lstmp_b200_get_info(lstmp_b200_handle_t h, lstmp_b200_info_t* inf
   info->max_frames = h->Tmax; info->sm_count = h->sm_count;
   info->ngroups = h->d.ngroups; info->ctas_per_group = h->d.ctas_per_group; info->streams_per_group = h->d.Sg;
   info->cells_per_cta = h->d.cpc; info->rcols_per_cta = h->d.rpc;
-  info->fwd_smem_bytes = h->rec_tma ? h->fwd_tma_smem : h->fwd_tc ? h->fwd_tc_smem : h->fwd_smem;
+  info->fwd_smem_bytes = h->rec_tma ? h->fwd_tma_smem : h->fwd_smem;
   info->bwd_smem_bytes = h->rec_tma ? h->bwd_tma_smem : h->bwd_smem;
   info->workspace_bytes = h->workspace_bytes;
   info->kernel_launches = h->launches;
   info->gemm_backend = h->gemm_backend;
   info->weights_streamed = h->streamed ? 1 : 0;
-  info->fwd_tensor_core = h->rec_tma ? 2 : h->fwd_tc ? 1 : 0;
+  info->fwd_tensor_core = h->rec_tma ? 2 : 0;
   info->bwd_tensor_core = h->rec_tma ? 2 : 0;
   if (h->rec_tma) {
     info->ngroups = h->ftm.G;

@@ -12,15 +12,18 @@
 // and the product is accumulated in FP32 in TMEM as  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b.
 //
 // Structure of one CTA (288 threads), one 128 x BN output tile:
-//   warps 0-7  : loader/transform -- coalesced LDG.128 of the fp32 operands (either storage
-//                order; m/n-contiguous sources are transposed in registers), split into hi/lo,
-//                STS.128 into UMMA canonical no-swizzle K-major shared-memory tiles,
-//                fence.proxy.async, mbarrier arrive.  After the
-//                main loop the same warps run the epilogue: tcgen05.ld -> alpha/beta/bias -> STG.
-//   warp 8     : TMEM allocation; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN,
-//                K=8) x 12 per 32-deep K block and tcgen05.commit onto the stage's "empty"
-//                mbarrier / the accumulator-ready mbarrier.
-// 3-stage shared-memory ring, mbarrier full/empty handshakes, accumulator in TMEM.
+//   warps 0-7  : loader/transform -- cp.async.cg (LDGSTS) of the fp32 operands (either storage order) into per-thread
+//                landing slots, 3 K blocks in flight; each thread reads its own 16-byte units back, transposes
+//                m/n-contiguous sources in registers, splits into hi/lo and stores them (STS.128) into SWIZZLE_128B
+//                K-major tiles; one mbarrier arrival per warp.  After the main loop the same warps run the epilogue:
+//                tcgen05.ld -> alpha/beta/bias -> STG.
+//   warp 8     : TMEM allocation; after its acquire-wait it executes the fence.proxy.async for the loaders' stores and
+//                issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 12 per 32-deep K block (whole warp on warp-uniform
+//                operands, elect.sync predication) and tcgen05.commit onto the stage's "empty" mbarrier / the
+//                accumulator-ready mbarrier.
+// 2-stage UMMA ring + 3 raw landing slots, mbarrier full/empty handshakes, accumulator in TMEM.
+// Since round 2 this kernel is the FALLBACK (LSTMP_B200_GEMM=1); the default is lstmp_gemm_hl.cu (pre-split bf16 hi/lo
+// tile images, bulk copies, no loader warps).
 #include <cstdlib>
 #include "lstmp_common.cuh"
 #include "lstmp_kernels.h"
@@ -180,9 +183,8 @@ struct Loader {
   }
 };
 
-// MODE: 0 = LDG.128 register prefetch, all 8 loader warps on every K block; 1 = cp.async landing slots (default);
-//       2 = "ping-pong": two groups of 4 loader warps take alternate K blocks (register loads), so that two K blocks are
-//           in progress at once (opt-in, LSTMP_B200_GEMM_LOADER=2; not yet validated on hardware)
+// MODE: 1 = cp.async landing slots (the only mode instantiated: 43 vs 52 us on the weight-gradient GEMMs against MODE 0,
+//       LDG.128 register prefetch; a "ping-pong" two-group loader was measured slower still in round 2 and removed)
 template <int BN, bool A_MN, bool B_MN, int MODE>
 struct Smem {
   static constexpr bool STAGED = (MODE == 1);
@@ -205,15 +207,9 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
   constexpr int NSTAGE = SM::NSTAGE;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // 1024-byte align the tile area (SWIZZLE_128B atoms)
-#ifdef LSTMP_TC_SHARED_SPACE
-  // Pointer arithmetic on the __shared__ array keeps the address space visible to the compiler: the loaders' accesses
-  // become STS.128 / LDS.128.  (Found at the end of round 1 by reading the SASS: with the integer round trip below
-  // every shared-memory access of this kernel is a GENERIC LD.E.128 / ST.E.128.  Not yet validated on hardware, hence
-  // opt-in: `make sts` builds _lib/liblstmp_b200_sts.so, select it with LSTMP_B200_LIB.)
+  // Pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space visible to the
+  // compiler: the loaders' accesses are STS.128 / LDS.128 instead of generic ST.E / LD.E (round 2: 47 vs 50 us in_diff)
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-#else
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-#endif
   uint8_t* raw = tiles + NSTAGE * SM::STAGE;
   uint64_t* full = reinterpret_cast<uint64_t*>(raw + (STAGED ? NRAW * SM::RAW : 0));
   uint64_t* empty = full + NSTAGE;
@@ -240,7 +236,7 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], MODE == 2 ? LOADERS / 64 : LOADERS / 32);
+      mbar_init(&full[s], LOADERS / 32);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum_ready, 1);
@@ -260,33 +256,7 @@ gemm_tc_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int K, float
 
   if (warp < 8) {
     // =============================== loader / transform ==================================
-    if constexpr (MODE == 2) {
-      // Two groups of 4 warps; group g loads, splits and stores the K blocks kb = g, g + 2, ... on its own (each thread
-      // owns twice as many units) and arrives with 4 warp arrivals.  With all 8 warps on every K block the block cannot
-      // complete faster than one warp's dependent chain load -> split -> wait for the stage -> store -> arrive.
-      constexpr int GT = LOADERS / 2;
-      const int grp = warp >> 2, gt = tid & (GT - 1);
-      Loader<BM, A_MN, GT> la;
-      Loader<BN, B_MN, GT> lb;
-      int kb = grp;
-      if (kb < nkb) {
-        la.load(A, lda, m0, M, kb * BK, K, gt);
-        lb.load(B, ldb, n0, N, kb * BK, K, gt);
-      }
-      for (; kb < nkb; kb += 2) {
-        const int s = kb % NSTAGE;
-        if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
-        uint8_t* st = tiles + (size_t)s * SM::STAGE;
-        la.store(st, st + SM::A_BYTES, gt);
-        lb.store(st + 2 * SM::A_BYTES, st + 2 * SM::A_BYTES + SM::B_BYTES, gt);
-        if (kb + 2 < nkb) {  // this group's next K block: in flight while the other group stores and the MMAs run
-          la.load(A, lda, m0, M, (kb + 2) * BK, K, gt);
-          lb.load(B, ldb, n0, N, (kb + 2) * BK, K, gt);
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&full[s]);
-      }
-    } else if constexpr (STAGED) {
+    if constexpr (STAGED) {
       Loader<BM, A_MN> la;
       Loader<BN, B_MN> lb;
   #pragma unroll
@@ -533,25 +503,8 @@ cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float a
   if (!al16(C)) return cudaSuccess;
   *handled = true;
   const bool small_n = (N <= 64);
-  // operand loader variant (LSTMP_B200_GEMM_LOADER): 1 = cp.async into raw landing slots (default; measured 43 vs 52 us
-  // on the weight-gradient GEMMs), 0 = LDG.128 into rotating register sets (also LSTMP_B200_GEMM_STAGED=0),
-  // 2 = ping-pong loader groups (opt-in, not yet validated on hardware)
-  static const int mode = [] {
-    const char* v = getenv("LSTMP_B200_GEMM_LOADER");
-    if (v && *v) {
-      const int m = atoi(v);
-      return (m >= 0 && m <= 2) ? m : 1;
-    }
-    const char* s = getenv("LSTMP_B200_GEMM_STAGED");
-    return (!(s && *s) || atoi(s) != 0) ? 1 : 0;
-  }();
-#define LSTMP_TC_CASE(BN_, AMN_, BMN_)                                                                                 \
-  return mode == 1 ? tc::launch_one<BN_, AMN_, BMN_, 1>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, \
-                                                        ws_floats, nlaunch)                                            \
-       : mode == 2 ? tc::launch_one<BN_, AMN_, BMN_, 2>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, \
-                                                        ws_floats, nlaunch)                                            \
-                   : tc::launch_one<BN_, AMN_, BMN_, 0>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, \
-                                                        ws_floats, nlaunch)
+#define LSTMP_TC_CASE(BN_, AMN_, BMN_) \
+  return tc::launch_one<BN_, AMN_, BMN_, 1>(C, ldc, M, N, K, alpha, A, lda, B, ldb, beta, bias, stream, ws, ws_floats, nlaunch)
   if (small_n) {
     if (!a_mn && !b_mn) LSTMP_TC_CASE(64, false, false);
     if (!a_mn && b_mn) LSTMP_TC_CASE(64, false, true);

@@ -68,35 +68,6 @@ int static_smem_reserve();
 int fwd_barriers(int T);
 int bwd_barriers(int T);
 
-// ---- tensor-core forward time loop (lstmp_recurrent_tc.cu) ------------------------------------------------
-// One stream group (all S <= 64 streams), nctas co-resident CTAs; CTA j owns cells [j*cpc, +cpc) and r columns
-// [j*rpc, +rpc).  The activations are the tcgen05 A operand (M = 128 rows = S "hi" rows then S "lo" rows of the
-// 3xTF32 split, streamed through a shared-memory ring), the CTA's weight slice is the stationary B operand
-// (rows = hi rows then lo rows, N = 16-aligned).  All offsets in bytes from the 128-byte aligned dynamic smem base.
-struct FwdTcParams {
-  int I, C, R, S, T;
-  int nctas, cpc, rpc;
-  int n_g, n_p;                 // MMA N for the gate / projection products
-  int nslot;                    // ring slots of [128 rows x 32 k]
-  int loader;                   // 1: cp.async landing slots + transform (default), 0: LDG.128 register prefetch,
-                                // 2: warp-per-chunk (opt-in, LSTMP_B200_TC_LOADER)
-  int stagger;                  // 1: CTA j starts its K-chunk walk at chunk j mod nch (spreads the L2 requests)
-  unsigned chunk_g, chunk_p;    // bytes of one 32-k tile of the stationary weight slices (SWIZZLE_128B)
-  unsigned off_bg, off_bp, off_ring, slot_bytes, off_red, off_stage, ldred, off_cprev, off_peep, off_bars;
-  const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
-  float *gifo, *cbuf, *hbuf, *mbuf, *rbuf, *out;
-  long long ld_out;
-  float *state_c, *state_r;
-  unsigned* bar;
-  unsigned bar_base;
-  int dbg;
-  long long* dbg_stamps;
-};
-// false when the shape is not eligible (S > 64, C or R not a multiple of 32, slices do not fit)
-bool fwd_tc_plan(int C, int R, int S, int nctas, size_t smem_limit, int loader, FwdTcParams* p, size_t* smem_bytes);
-cudaError_t fwd_tc_set_smem_limit(size_t bytes);
-cudaError_t launch_fwd_tc(const FwdTcParams& p, size_t smem_bytes, cudaStream_t stream);
-
 // ---- TMA-fed tcgen05 time loops, forward and backward (lstmp_recurrent_tma.cu) --------------------------------
 // Activations cross the chip as bf16 hi/lo pairs written by their producer into global "tile image" arrays (per 64-k
 // chunk the ready-made SWIZZLE_128B shared-memory image of [hi rows | lo rows]) and are pulled into a shared-memory

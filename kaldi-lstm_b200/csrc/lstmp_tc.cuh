@@ -1,9 +1,10 @@
-// tcgen05 / TMEM / UMMA-descriptor helpers shared by the tensor-core GEMM (lstmp_gemm_tc.cu) and the
-// tensor-core time loop (lstmp_recurrent_tc.cu).  sm_100a only.
+// tcgen05 / TMEM / UMMA-descriptor helpers shared by the tensor-core GEMMs (lstmp_gemm_hl.cu, lstmp_gemm_tc.cu) and
+// the tensor-core time loops (lstmp_recurrent_tma.cu).  sm_100a only.
 //
-// Shared-memory operand layout used everywhere (the one validated on hardware): UMMA canonical K-major, no swizzle,
-//   off(row, k) = (k/4)*LBO + (row/8)*SBO + (row%8)*16 + (k%4)*4   bytes, with SBO = 128,
-// i.e. each 16-byte K chunk ("slab") is a dense [rows][4 floats] array and consecutive slabs are LBO bytes apart.
+// Shared-memory operand layout used everywhere: SWIZZLE_128B K-major tiles -- rows of 128 bytes along K (32 tf32 or
+// 64 bf16), 8-row groups of 1024 bytes, tile bases 1024-byte aligned, the 16-byte unit index of a row XORed with
+// (row & 7); see sw128_off / make_desc_sw128 below.  (make_desc, the no-swizzle form, is kept for the microbenchmarks
+// under tools/.)
 #pragma once
 #include "lstmp_common.cuh"
 
