@@ -79,6 +79,8 @@ struct FwdTmaParams {
   int n_g, n_p;                 // MMA N of the gate / projection products
   int nch_g, nch_p;             // 64-k chunks of the two contractions (K = R, K = C)
   int nslot, nprod, stagger;
+  int gt;                       // 64-k tiles per ring slot = per bulk copy
+  unsigned slot_bytes;
   unsigned chunk_g, chunk_p;    // bytes of one 64-k tile of the stationary weight slices
   unsigned off_bg, off_bp, off_ring, off_red, ldred, off_cprev, off_peep, off_bars;
   const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
@@ -99,6 +101,8 @@ struct BwdTmaParams {
   int n_a, n_b;                 // MMA N of the d_r / d_m products
   int nch_a, nch_b;             // 64-k chunks: K = 4C (split over the kp ranks of a cluster), K = R
   int nslot, nprod, stagger;
+  int gt;                       // 64-k tiles per ring slot = per bulk copy
+  unsigned slot_bytes;
   unsigned chunk_a, chunk_b;
   unsigned off_ba, off_bb, off_ring, off_red, ldred, off_dgn, off_dcn, off_acc7, off_peep, off_bars;
   const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;

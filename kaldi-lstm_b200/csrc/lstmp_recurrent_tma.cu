@@ -33,7 +33,7 @@ namespace lstmp {
 
 namespace tm {
 constexpr int KC = 64;                       // bf16 k per ring slot row (128 bytes): 4 MMAs of K = 16
-constexpr uint32_t SLOT_BYTES = 128 * 128;   // [128 rows][128 B], SWIZZLE_128B; hi rows at 0, lo rows at row Sg
+constexpr uint32_t TILE_MAX = 128 * 128;     // one tile: [<= 128 rows][128 B], SWIZZLE_128B; hi rows at 0, lo rows at row Sg
 constexpr int NPROD = 3;                     // TMA producer warps (8, 10, 11): chunk c is issued by producer c mod 3
 constexpr int MAX_SLOTS = 8;
 constexpr uint32_t TMEM_COLS = 512;          // whole TMEM: the CTA is alone on its SM
@@ -106,6 +106,8 @@ struct Ring {
   uint8_t* ring;
   uint64_t *full, *empty, *accum, *gridok;
   int nslot, nprod;
+  int gt;               // tiles (64-k chunks) per ring slot = per bulk copy
+  uint32_t slot_bytes;  // gt * tile bytes
 };
 
 // Grid barrier between the co-resident CTAs of one stream group, split into arrive / wait and run by ONE thread per
@@ -150,6 +152,7 @@ __device__ __forceinline__ bool is_sync_thread() { return threadIdx.x == kProduc
 // bit-reproducible; spreads the CTAs' requests for the same lines over time).  grid_wait: the operand was written by
 // other CTAs before the grid barrier this CTA last arrived at -- the producer waits for it before its first copy.
 // Every thread of the CTA calls this (CTA-uniform arguments); contains one __syncthreads at the end.
+template <int GT>  // tiles per ring slot / bulk copy (compile time: the MMA burst of a slot is fully unrolled)
 __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& gs, bool grid_wait,
                                             const uint8_t* img, int Sg, int kc0, int nch, int rot,
                                             uint32_t b_addr, uint32_t chunk_b, uint32_t idesc, uint32_t tmem_d, int nh,
@@ -157,6 +160,10 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& 
   // warp index through a shuffle: provably warp-uniform for ptxas (UMMA operands stay in uniform registers)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int nslot = rg.nslot;
+  constexpr int gt = GT;
+  const int ngr = (nch + gt - 1) / gt;  // pipeline steps: groups of up to gt consecutive tiles, one bulk copy each
+  rot = rot % ngr;                       // the stagger rotates the walk over the groups
+  const uint32_t tile_bytes = (uint32_t)(((2 * Sg + 7) & ~7) * 128);
   uint32_t slot = ps.cc % (uint32_t)nslot, use = ps.cc / (uint32_t)nslot;
   // With fewer ring slots than producers a producer could lap the parity of a slot's "empty" barrier (it would test
   // the phase two uses back): never more producers than slots.
@@ -164,10 +171,11 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& 
   const int prod = warp == kProducerWarp ? 0 : warp == kProducerWarp + 2 ? 1 : warp == kProducerWarp + 3 ? 2 : -1;
   if (prod >= 0 && prod < nprod) {
     // ------------------------------ TMA producers --------------------------------------------
-    // One 1-D bulk copy (cp.async.bulk, SASS UBLKCP) per chunk: the global array already holds the swizzled tile
-    // image.  Tensor-map copies (cp.async.bulk.tensor, 2-D / 3-D boxes of 128-byte rows) were measured first and
-    // delivered one row per ~3.5 cycles (36-43 B/clk per SM, profiles/r2_stamps_*_tensormap.txt), below what L2 gives
-    // this all-gather pattern.  The chunks are dealt round-robin to three threads in three warps.
+    // One 1-D bulk copy (cp.async.bulk, SASS UBLKCP) per GROUP of gt tiles: the global array already holds the
+    // swizzled tile images back to back.  A copy costs ~400 cycles of latency in the SM's copy unit whatever its size
+    // (measured with 8 KB and 16 KB copies, and with tensor-map copies of 128-byte rows: 36-43 B/clk per SM,
+    // profiles/r2_stamps_*_tensormap.txt), so fewer, larger copies are what helps; the groups are dealt round-robin to
+    // up to three threads in three warps.
     if (lane == 0) {
       if (grid_wait) {
         if (prod == 0) {
@@ -178,14 +186,14 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& 
         }
       }
       const uint32_t ring_s = smem_u32(rg.ring);
-      const uint32_t bytes = (uint32_t)(2 * Sg * 128);
-      const uint32_t tile_bytes = (uint32_t)(((2 * Sg + 7) & ~7) * 128);
-      for (int c = prod; c < nch; c += nprod) {
+      for (int c = prod; c < ngr; c += nprod) {
         const uint32_t idx = ps.cc + (uint32_t)c, sl = idx % (uint32_t)nslot, us = idx / (uint32_t)nslot;
         if (us > 0) mbar_wait(&rg.empty[sl], (us - 1) & 1);
-        const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
+        const int ge = (c + rot < ngr) ? c + rot : c + rot - ngr;
+        const int t0 = ge * gt, nt = min(gt, nch - t0);
+        const uint32_t bytes = (uint32_t)nt * tile_bytes;
         mbar_arrive_expect_tx(&rg.full[sl], bytes);
-        tma_bulk_g2s_u32(ring_s + sl * SLOT_BYTES, img + (size_t)(kc0 + ce) * tile_bytes, bytes, &rg.full[sl]);
+        tma_bulk_g2s_u32(ring_s + sl * rg.slot_bytes, img + (size_t)(kc0 + t0) * tile_bytes, bytes, &rg.full[sl]);
       }
       stamp(203);
     }
@@ -193,25 +201,31 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& 
   } else if (warp == kIssuerWarp) {
     // ------------------------------ MMA issuer -----------------------------------------------
     const uint32_t ring_s = smem_u32(rg.ring);
-    for (int c = 0; c < nch; ++c) {
+    for (int c = 0; c < ngr; ++c) {
       mbar_wait(&rg.full[slot], use & 1);
       if (c == 0) stamp(210);
       tc::tc_fence_after();
       {
         // the whole warp runs the burst on warp-uniform operands; elect.sync predicates the instructions (lstmp_tc.cuh)
-        const uint32_t a0 = ring_s + slot * SLOT_BYTES;
-        const int ce = (c + rot < nch) ? c + rot : c + rot - nch;
-        const uint32_t b0 = b_addr + (uint32_t)ce * chunk_b;
+        const int ge = (c + rot < ngr) ? c + rot : c + rot - ngr;
+        const int t0 = ge * gt, nt = min(gt, nch - t0);
 #pragma unroll
-        for (int j = 0; j < KC / 16; ++j) {
-          // MMA j covers the 16-byte units 2j, 2j+1 of the 128-byte rows (K = 16 bf16 per instruction)
-          const uint64_t da = tc::make_desc_sw128(a0 + 32 * j);
-          const uint64_t db = tc::make_desc_sw128(b0 + 32 * j);
-          if (tc::elect_one()) mma_bf16(tmem_d, da, db, idesc, (c | j) ? 1u : 0u);
+        for (int t = 0; t < GT; ++t) {
+          if (t < nt) {  // (warp-uniform; only the last group of a product can be short)
+            const uint32_t a0 = ring_s + slot * rg.slot_bytes + (uint32_t)t * tile_bytes;
+            const uint32_t b0 = b_addr + (uint32_t)(t0 + t) * chunk_b;
+#pragma unroll
+            for (int j = 0; j < KC / 16; ++j) {
+              // MMA j covers the 16-byte units 2j, 2j+1 of the 128-byte rows (K = 16 bf16 per instruction)
+              const uint64_t da = tc::make_desc_sw128(a0 + 32 * j);
+              const uint64_t db = tc::make_desc_sw128(b0 + 32 * j);
+              if (tc::elect_one()) mma_bf16(tmem_d, da, db, idesc, (c | t | j) ? 1u : 0u);
+            }
+          }
         }
         if (tc::elect_one()) {
           tc::umma_commit(&rg.empty[slot]);             // frees the slot once these MMAs have read it
-          if (c == nch - 1) tc::umma_commit(rg.accum);  // accumulator complete
+          if (c == ngr - 1) tc::umma_commit(rg.accum);  // accumulator complete
         }
       }
       __syncwarp();
@@ -243,7 +257,7 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& 
   }
   __syncthreads();
   tc::tc_fence_after();
-  ps.cc += (uint32_t)nch;
+  ps.cc += (uint32_t)ngr;
   ps.acc += 1;
 }
 
@@ -267,6 +281,7 @@ __device__ __forceinline__ void tma_bulk_g2s_u32(uint32_t smem_dst, const void* 
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
+template <int GT>
 __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid_constant__ FwdTmaParams p) {
   using namespace tm;
   extern __shared__ __align__(16) uint8_t smem_raw_tma[];
@@ -286,6 +301,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
   rg.gridok = bars + 2 * MAX_SLOTS + 1;
   rg.nslot = p.nslot;
   rg.nprod = p.nprod;
+  rg.gt = p.gt;
+  rg.slot_bytes = p.slot_bytes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -403,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
         xo = gp[3 * C];
       }
       // gifo(t) += r(t-1) * W_gifo_r^T                                       (LPS.h:275)
-      tma_product(ps, rg, gs, true, rhl, Sg, 0, p.nch_g, rot_g, bg_s, p.chunk_g, idesc_g, tmem_base + COL_A,
+      tma_product<GT>(ps, rg, gs, true, rhl, Sg, 0, p.nch_g, rot_g, bg_s, p.chunk_g, idesc_g, tmem_base + COL_A,
                   4 * cpc, 4 * nc, red, ldred);
       stamp(11);
       // pass 1: the cell update; only m(t) hi/lo -- what the other CTAs wait for -- is stored before the arrive
@@ -465,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
     }
     // ================= phase 2: projection r(t) = m(t) * W_r_m^T for my columns (LPS.h:312) ==
     if (nr > 0) {
-      tma_product(ps, rg, gs, true, mhl, Sg, 0, p.nch_p, rot_p, bp_s, p.chunk_p, idesc_p, tmem_base + COL_B,
+      tma_product<GT>(ps, rg, gs, true, mhl, Sg, 0, p.nch_p, rot_p, bp_s, p.chunk_p, idesc_p, tmem_base + COL_B,
                   rpc, nr, red, ldred);
       stamp(22);
       for (int idx = tid; idx < Sg * nr; idx += kThreads) {
@@ -512,6 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_fwd_tma_kernel(const __grid
 // =====================================================================================================================
 // backward
 // =====================================================================================================================
+template <int GT>
 __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid_constant__ BwdTmaParams p) {
   using namespace tm;
   extern __shared__ __align__(16) uint8_t smem_raw_tma[];
@@ -532,6 +550,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
   rg.gridok = bars + 2 * MAX_SLOTS + 1;
   rg.nslot = p.nslot;
   rg.nprod = p.nprod;
+  rg.gt = p.gt;
+  rg.slot_bytes = p.slot_bytes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_SLOTS + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -645,7 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       }
       if (have_next) {
         if (nka > 0) {
-          tma_product(ps, rg, gs, true, dghl, Sg, ks, nka, rot_a, ba_s, p.chunk_a, idesc_a,
+          tma_product<GT>(ps, rg, gs, true, dghl, Sg, ks, nka, rot_a, ba_s, p.chunk_a, idesc_a,
                       tmem_base + COL_A, rpb, nn, red, ldred);
         } else {
           if (is_sync_thread()) gs.wait();
@@ -703,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
           yv[rd][7] = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;
         }
       }
-      tma_product(ps, rg, gs, true, drhl, Sg, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b,
+      tma_product<GT>(ps, rg, gs, true, drhl, Sg, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b,
                   tmem_base + COL_B, cpc, nc, red, ldred);
       stamp(45);
       for (int idx = tid; idx < Sg * nc; idx += kThreads) {
@@ -800,10 +820,37 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
 // host side
 // ------------------------------------------------------------------------------------------------
 static size_t round1k(size_t b) { return (b + 1023) & ~size_t(1023); }
+static int max_slots();
 static int num_producers() {  // LSTMP_B200_TMA_PRODUCERS: 1..3 producer warps (default 3)
   const char* v = getenv("LSTMP_B200_TMA_PRODUCERS");
   const int n = (v && *v) ? atoi(v) : tm::NPROD;
   return n < 1 ? 1 : n > tm::NPROD ? tm::NPROD : n;
+}
+// 64-k tiles per bulk copy / ring slot: 4, 2 or 1.  Forward default 4 (LSTMP_B200_TMA_GROUP_TILES), backward default 2
+// (LSTMP_B200_TMA_GROUP_TILES_BWD; its shared memory holds two weight slices and leaves room for a short ring only).
+// Measured at cfg3 (us per launch, forward / backward): 1 tile 208 / 290, 2 tiles 191 / 271, 4 tiles 182 / 278 (G = 1).
+static int group_tiles(bool bwd) {
+  const char* v = getenv(bwd ? "LSTMP_B200_TMA_GROUP_TILES_BWD" : "LSTMP_B200_TMA_GROUP_TILES");
+  const int n = (v && *v) ? atoi(v) : (bwd ? 2 : 4);
+  return n >= 4 ? 4 : n >= 2 ? 2 : 1;
+}
+// ring geometry: the most tiles per slot (<= the wish) that still leaves two slots in `avail` bytes
+static bool ring_plan(size_t avail, int Sg, bool bwd, int* gt, unsigned* slot_bytes, int* nslot) {
+  const size_t tile = (size_t)((2 * Sg + 7) & ~7) * 128;
+  for (int g = group_tiles(bwd); g >= 1; g >>= 1) {
+    const size_t sb = g * tile;
+    // (an MMA reads 128 rows of a tile whatever Sg is: a slot is rounded up so that the over-read stays inside it)
+    const size_t need = sb + (tile < tm::TILE_MAX ? tm::TILE_MAX - tile : 0);
+    if (avail >= 2 * need) {
+      int n = (int)(avail / need);
+      if (n > max_slots()) n = max_slots();
+      *gt = g;
+      *slot_bytes = (unsigned)((need + 1023) & ~size_t(1023));
+      *nslot = n;
+      return true;
+    }
+  }
+  return false;
 }
 static int max_slots() {  // LSTMP_B200_TMA_SLOTS caps the ring depth (tests: the 2-slot ring of the tightest shapes)
   const char* v = getenv("LSTMP_B200_TMA_SLOTS");
@@ -847,12 +894,15 @@ bool fwd_tma_plan(int C, int R, int S, int G, int nctas, size_t smem_limit, FwdT
   const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)Sg * cpc * 4) + 1024 /* peepholes */ +
                       1024 /* barriers + tmem slot */;
   const size_t reserve = 1024 /* base alignment */ + (size_t)static_smem_reserve();
-  if (smem_limit < off + tail + reserve + (size_t)2 * SLOT_BYTES) return false;
-  int nslot = (int)((smem_limit - off - tail - reserve) / SLOT_BYTES);
-  if (nslot > max_slots()) nslot = max_slots();
+  if (smem_limit < off + tail + reserve) return false;
+  int nslot = 0, gt = 1;
+  unsigned slot_bytes = 0;
+  if (!ring_plan(smem_limit - off - tail - reserve, Sg, false, &gt, &slot_bytes, &nslot)) return false;
   p->nslot = nslot;
   p->nprod = num_producers();
-  off += (size_t)nslot * SLOT_BYTES;
+  p->gt = gt;
+  p->slot_bytes = slot_bytes;
+  off += (size_t)nslot * slot_bytes;
   p->off_red = take((size_t)128 * ldred * 4);
   p->off_cprev = take((size_t)Sg * cpc * 4);
   p->off_peep = take((size_t)3 * cpc * 4);
@@ -899,12 +949,15 @@ bool bwd_tma_plan(int C, int R, int S, int G, int nctas, int kp, size_t smem_lim
   const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)2 * Sg * cpc * 4) +
                       round1k((size_t)Sg * cpc * 4) + round1k((size_t)Sg * cpc * 7 * 4) + 1024 + 1024;
   const size_t reserve = 1024 + (size_t)static_smem_reserve();
-  if (smem_limit < off + tail + reserve + (size_t)2 * SLOT_BYTES) return false;
-  int nslot = (int)((smem_limit - off - tail - reserve) / SLOT_BYTES);
-  if (nslot > max_slots()) nslot = max_slots();
+  if (smem_limit < off + tail + reserve) return false;
+  int nslot = 0, gt = 1;
+  unsigned slot_bytes = 0;
+  if (!ring_plan(smem_limit - off - tail - reserve, Sg, true, &gt, &slot_bytes, &nslot)) return false;
   p->nslot = nslot;
   p->nprod = num_producers();
-  off += (size_t)nslot * SLOT_BYTES;
+  p->gt = gt;
+  p->slot_bytes = slot_bytes;
+  off += (size_t)nslot * slot_bytes;
   p->off_red = take((size_t)128 * ldred * 4);
   p->off_dgn = take((size_t)2 * Sg * cpc * 4);
   p->off_dcn = take((size_t)Sg * cpc * 4);
@@ -923,15 +976,19 @@ cudaError_t tma_set_smem_limits(size_t fwd_bytes, size_t bwd_bytes) {
   if (e != cudaSuccess) return e;
   dev &= 63;
   if (fwd_bytes > cur_f[dev]) {
-    e = cudaFuncSetAttribute((const void*)lstmp_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)fwd_bytes);
-    if (e != cudaSuccess) return e;
+    for (const void* fn : {(const void*)lstmp_fwd_tma_kernel<1>, (const void*)lstmp_fwd_tma_kernel<2>,
+                           (const void*)lstmp_fwd_tma_kernel<4>}) {
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_bytes);
+      if (e != cudaSuccess) return e;
+    }
     cur_f[dev] = fwd_bytes;
   }
   if (bwd_bytes > cur_b[dev]) {
-    e = cudaFuncSetAttribute((const void*)lstmp_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)bwd_bytes);
-    if (e != cudaSuccess) return e;
+    for (const void* fn : {(const void*)lstmp_bwd_tma_kernel<1>, (const void*)lstmp_bwd_tma_kernel<2>,
+                           (const void*)lstmp_bwd_tma_kernel<4>}) {
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_bytes);
+      if (e != cudaSuccess) return e;
+    }
     cur_b[dev] = bwd_bytes;
   }
   return cudaSuccess;
@@ -951,7 +1008,7 @@ int bwd_tma_max_ctas(int kp, size_t smem_bytes, int max_ctas) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int ncl = 0;
-  if (cudaOccupancyMaxActiveClusters(&ncl, (const void*)lstmp_bwd_tma_kernel, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&ncl, (const void*)lstmp_bwd_tma_kernel<1>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -963,7 +1020,9 @@ int bwd_tma_max_ctas(int kp, size_t smem_bytes, int max_ctas) {
 cudaError_t launch_fwd_tma(const FwdTmaParams& p, size_t smem_bytes, cudaStream_t stream) {
   void* args[] = {(void*)&p};
   dim3 grid(p.nctas), block(kThreads);
-  return cudaLaunchCooperativeKernel((const void*)lstmp_fwd_tma_kernel, grid, block, args, smem_bytes, stream);
+  const void* fn = p.gt == 4 ? (const void*)lstmp_fwd_tma_kernel<4>
+                   : p.gt == 2 ? (const void*)lstmp_fwd_tma_kernel<2> : (const void*)lstmp_fwd_tma_kernel<1>;
+  return cudaLaunchCooperativeKernel(fn, grid, block, args, smem_bytes, stream);
 }
 
 cudaError_t launch_bwd_tma(const BwdTmaParams& p, size_t smem_bytes, cudaStream_t stream) {
@@ -972,6 +1031,8 @@ cudaError_t launch_bwd_tma(const BwdTmaParams& p, size_t smem_bytes, cudaStream_
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
+  void (*fn)(const BwdTmaParams) = p.gt == 4 ? lstmp_bwd_tma_kernel<4> : p.gt == 2 ? lstmp_bwd_tma_kernel<2>
+                                                                                   : lstmp_bwd_tma_kernel<1>;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)p.kp;
@@ -990,13 +1051,13 @@ cudaError_t launch_bwd_tma(const BwdTmaParams& p, size_t smem_bytes, cudaStream_
   }();
   if (coop_ok) {
     cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstmp_bwd_tma_kernel, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
     if (e == cudaSuccess) return e;
     cudaGetLastError();
     coop_ok = 0;
   }
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, lstmp_bwd_tma_kernel, p);
+  return cudaLaunchKernelEx(&cfg, fn, p);
 }
 
 }  // namespace lstmp
