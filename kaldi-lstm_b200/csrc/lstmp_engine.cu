@@ -45,6 +45,19 @@ static int fail(int code, const char* fmt, ...) {
       return fail((int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// Every entry point runs on the handle's device and restores the caller's current device on return (a process may
+// hold engines on several GPUs; torch's notion of the current device must not change under it).
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int d) : dev(d) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != d) err = cudaSetDevice(d);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
 struct lstmp_b200_engine {
   int I = 0, C = 0, R = 0, S = 0, Tmax = 0, device = 0, sm_count = 0;
   size_t nparams = 0;
@@ -165,7 +178,7 @@ static int alloc_f(float** p, size_t n, size_t* total) {
 
 extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DeviceGuard device_guard(h->device);
   float* bufs[] = {h->params, h->corr, h->grads, h->state_c, h->state_r, h->gifo, h->cbuf, h->hbuf,
                    h->mbuf,   h->rbuf, h->dgifo, h->dr,      h->scratch, h->small_grads, h->dm, h->dc2, h->gemm_ws};
   for (float* b : bufs)
@@ -206,7 +219,8 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
   if (e != cudaSuccess || ndev == 0)
     return fail(LSTMP_B200_ENODEV, "no CUDA device: %s (this engine has no CPU path)", cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return fail(LSTMP_B200_EINVAL, "device %d out of range (%d devices)", device, ndev);
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard device_guard(device);
+  CUDA_TRY(device_guard.err);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
@@ -361,11 +375,11 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
   return 0;
 }
 
-#define CHECK_H(h)                                               \
-  do {                                                           \
-    if (!(h)) return fail(LSTMP_B200_EINVAL, "NULL handle");     \
-    CUDA_TRY(cudaSetDevice((h)->device));                        \
-  } while (0)
+#define CHECK_H(h)                                                                                        \
+  if (!(h)) return fail(LSTMP_B200_EINVAL, "NULL handle");                                                \
+  DeviceGuard device_guard__((h)->device);                                                                \
+  if (device_guard__.err != cudaSuccess)                                                                  \
+    return fail((int)device_guard__.err, "cudaSetDevice(%d): %s", (h)->device, cudaGetErrorString(device_guard__.err))
 
 extern "C" int lstmp_b200_num_params(lstmp_b200_handle_t h, size_t* n) {
   if (!h || !n) return fail(LSTMP_B200_EINVAL, "NULL argument");

@@ -156,10 +156,19 @@ class B200LstmProjectedStreams : public UpdatableComponent {
                                    in_diff ? B200DevPtr(in_diff) : NULL, in_diff ? in_diff->Stride() : 0,
                                    in.NumRows(), NULL));
   }
+  // PAIRING CONTRACT: the reference accumulates momentum in BackpropagateFnc (corr = G + mmt*corr, LPS.h:465-487) and
+  // Update only applies param -= lr*corr.  Here BackpropagateFnc leaves the FRESH gradient G (so that it can be
+  // all-reduced) and Update does both steps: identical under the trainer's Propagate -> Backpropagate -> Update order;
+  // GetGradient / InfoGradient between Backpropagate and Update still show the previous chunk's corr, and two
+  // Backpropagate calls without an Update keep only the second gradient.  (INTEGRATION.md.)
   void Update(const CuMatrixBase<BaseFloat>&, const CuMatrixBase<BaseFloat>&) {  // LPS.h:465-487 + :501-512
     if (comm_) Check(lstmp_b200_allreduce_grads_nccl(engine_, comm_, NULL));  // data-parallel: sum fresh gradients
-    Check(lstmp_b200_update(engine_, opts_.learn_rate, opts_.momentum, NULL));
+    if (max_grad_ > 0)  // the standard single-stream version's element-wise clip (nnet-lstm-projected.h:469-493)
+      Check(lstmp_b200_update_clipped(engine_, opts_.learn_rate, opts_.momentum, max_grad_, NULL));
+    else
+      Check(lstmp_b200_update(engine_, opts_.learn_rate, opts_.momentum, NULL));
   }
+  void SetMaxGrad(BaseFloat max_grad) { max_grad_ = max_grad; }
 
   // Data-parallel training: an ncclComm_t shared by the ranks that shard the streams.
   void SetNcclComm(void* comm) { comm_ = comm; }
@@ -192,7 +201,8 @@ class B200LstmProjectedStreams : public UpdatableComponent {
 
   int32 ncell_, nrecur_, nstream_, max_frames_;
   lstmp_b200_handle_t engine_;
-  void* comm_ = NULL;
+  void* comm_ = NULL;           // per process; NOT carried over by Copy() -- call SetNcclComm on the copy
+  BaseFloat max_grad_ = 0;
 };
 
 }  // namespace nnet1
