@@ -120,6 +120,12 @@ int lstmp_b200_update(lstmp_b200_handle_t h, float learn_rate, float momentum, v
  * `stream`.  NCCL is resolved at run time with dlopen("libnccl.so.2"); returns
  * LSTMP_B200_EUNSUPPORTED when it cannot be loaded. */
 int lstmp_b200_allreduce_grads_nccl(lstmp_b200_handle_t h, void* nccl_comm, void* stream);
+/* Overlapped exchange: with a communicator set, lstmp_b200_backpropagate itself sums each gradient block over the ranks
+ * on `comm_stream` as soon as the kernel that produced it has been enqueued -- w_gifo_x after its GEMM, then
+ * w_gifo_r | bias | peepholes, then w_r_m -- so that the all-reduce of a block runs under the following gradient GEMMs
+ * (and under the backward pass of the layers below); lstmp_b200_update[_clipped] waits for the last block.  Every rank
+ * must call backpropagate on its engines in the same order.  nccl_comm == NULL switches it off. */
+int lstmp_b200_set_nccl(lstmp_b200_handle_t h, void* nccl_comm, void* comm_stream);
 
 /* Introspection for benchmarks and tests. */
 typedef struct {

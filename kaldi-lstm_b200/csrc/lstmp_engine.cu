@@ -88,6 +88,11 @@ struct lstmp_b200_engine {
   unsigned long long launches = 0;
   int gemm_backend = 0;
   HlWorkspace hlws;
+  // data-parallel exchange overlapped with the backward pass (lstmp_b200_set_nccl)
+  void* nccl_comm = nullptr;
+  cudaStream_t nccl_stream = nullptr;
+  cudaEvent_t ev_block = nullptr, ev_comm_done = nullptr;
+  bool exchange_pending = false;
   long long* dbg_stamps = nullptr;
   // weights-streamed mode: slices do not fit in shared memory -> per-step GEMMs + elementwise kernels
   bool streamed = false;
@@ -184,6 +189,8 @@ extern "C" int lstmp_b200_destroy(lstmp_b200_handle_t h) {
   for (float* b : bufs)
     if (b) cudaFree(b);
   if (h->bar) cudaFree(h->bar);
+  if (h->ev_block) cudaEventDestroy(h->ev_block);
+  if (h->ev_comm_done) cudaEventDestroy(h->ev_comm_done);
   gemm_hl_free(&h->hlws);
   if (h->rhl) cudaFree(h->rhl);  // one allocation holds rhl | mhl | dghl | drhl
   for (auto& e : h->events) {  // timing enabled but never read back
@@ -654,6 +661,37 @@ extern "C" int lstmp_b200_propagate(lstmp_b200_handle_t h, const float* in, size
   return 0;
 }
 
+// ---- NCCL, resolved at run time ------------------------------------------------------------
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static int nccl_sum(float* buf, size_t count, void* comm, cudaStream_t stream) {
+  static nccl_allreduce_fn fn = nullptr;
+  if (!fn) {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(LSTMP_B200_EUNSUPPORTED, "dlopen(libnccl.so.2): %s", dlerror());
+    fn = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+    if (!fn) return fail(LSTMP_B200_EUNSUPPORTED, "ncclAllReduce not found");
+  }
+  // ncclFloat32 = 7, ncclSum = 0
+  int rc = fn(buf, buf, count, 7, 0, comm, stream);
+  if (rc != 0) return fail(LSTMP_B200_EUNSUPPORTED, "ncclAllReduce returned %d", rc);
+  return 0;
+}
+// Overlapped exchange (lstmp_b200_set_nccl): the gradient block [off, off + count) of the arena is final on the compute
+// stream `st` -- sum it over the ranks on the communication stream while the remaining gradient GEMMs run.
+static int exchange_block(lstmp_b200_handle_t h, size_t off, size_t count, cudaStream_t st, bool last) {
+  if (!h->nccl_comm) return 0;
+  CUDA_TRY(cudaEventRecord(h->ev_block, st));
+  CUDA_TRY(cudaStreamWaitEvent(h->nccl_stream, h->ev_block, 0));
+  int rc = nccl_sum(h->grads + off, count, h->nccl_comm, h->nccl_stream);
+  if (rc) return rc;
+  if (last) {
+    CUDA_TRY(cudaEventRecord(h->ev_comm_done, h->nccl_stream));
+    h->exchange_pending = true;
+  }
+  return 0;
+}
+
 extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, size_t ld_in, const float* out_diff,
                                         size_t ld_od, float* in_diff, size_t ld_id, int num_rows, void* stream) {
   CHECK_H(h);
@@ -765,19 +803,32 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
   if ((rc = gemm(h, 4, h->grads + h->off_wx, I, 4 * C, I, num_rows, 1.f, h->dgifo, 4 * C, 1, in, (long long)ld_in, 0,
                  0.f, nullptr, st)))
     return rc;
+  if ((rc = exchange_block(h, h->off_wx, (size_t)4 * C * I, st, false))) return rc;
   // G(w_gifo_r) = DGIFO[1..T]^T * R[0..T-1]                                  (LPS.h:471)
   if ((rc = gemm(h, 4, h->grads + h->off_wr, R, 4 * C, R, num_rows, 1.f, h->dgifo, 4 * C, 1, h->rbuf, R, 0, 0.f,
                  nullptr, st, /*reuse_a: DGIFO^T was split for the previous GEMM*/ true)))
     return rc;
+  // w_gifo_r | bias | peepholes are contiguous in the arena; bias / peepholes were written before the GEMMs
+  if ((rc = exchange_block(h, h->off_wr, h->off_wm - h->off_wr, st, false))) return rc;
   // G(w_r_m) = DR[1..T]^T * M[1..T]                                          (LPS.h:486)
   if ((rc = gemm(h, 4, h->grads + h->off_wm, C, R, C, num_rows, 1.f, h->dr, R, 1, h->mbuf, C, 0, 0.f, nullptr, st)))
     return rc;
+  if ((rc = exchange_block(h, h->off_wm, (size_t)R * C, st, true))) return rc;
   h->have_bwd = true;
+  return 0;
+}
+
+static int wait_exchange(lstmp_b200_handle_t h, cudaStream_t st) {
+  if (h->exchange_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_comm_done, 0));
+    h->exchange_pending = false;
+  }
   return 0;
 }
 
 extern "C" int lstmp_b200_update(lstmp_b200_handle_t h, float learn_rate, float momentum, void* stream) {
   CHECK_H(h);
+  if (int rc = wait_exchange(h, (cudaStream_t)stream)) return rc;
   {
     Timed tm(h, 6, (cudaStream_t)stream);
     CUDA_TRY(launch_update(h->params, h->corr, h->grads, h->nparams, learn_rate, momentum, 0.f, (cudaStream_t)stream));
@@ -789,6 +840,7 @@ extern "C" int lstmp_b200_update(lstmp_b200_handle_t h, float learn_rate, float 
 extern "C" int lstmp_b200_update_clipped(lstmp_b200_handle_t h, float learn_rate, float momentum, float max_grad,
                                          void* stream) {
   CHECK_H(h);
+  if (int rc = wait_exchange(h, (cudaStream_t)stream)) return rc;
   {
     Timed tm(h, 6, (cudaStream_t)stream);
     CUDA_TRY(launch_update(h->params, h->corr, h->grads, h->nparams, learn_rate, momentum, max_grad > 0.f ? max_grad : 0.f,
@@ -798,22 +850,21 @@ extern "C" int lstmp_b200_update_clipped(lstmp_b200_handle_t h, float learn_rate
   return 0;
 }
 
-// ---- NCCL, resolved at run time ------------------------------------------------------------
-typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 extern "C" int lstmp_b200_allreduce_grads_nccl(lstmp_b200_handle_t h, void* comm, void* stream) {
   CHECK_H(h);
   if (!comm) return fail(LSTMP_B200_EINVAL, "NULL ncclComm_t");
-  static nccl_allreduce_fn fn = nullptr;
-  if (!fn) {
-    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) return fail(LSTMP_B200_EUNSUPPORTED, "dlopen(libnccl.so.2): %s", dlerror());
-    fn = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
-    if (!fn) return fail(LSTMP_B200_EUNSUPPORTED, "ncclAllReduce not found");
+  return nccl_sum(h->grads, h->nparams, comm, (cudaStream_t)stream);
+}
+
+extern "C" int lstmp_b200_set_nccl(lstmp_b200_handle_t h, void* comm, void* comm_stream) {
+  CHECK_H(h);
+  if (comm && !h->ev_block) {
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_block, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_comm_done, cudaEventDisableTiming));
   }
-  // ncclFloat32 = 7, ncclSum = 0
-  int rc = fn(h->grads, h->grads, h->nparams, 7, 0, comm, (cudaStream_t)stream);
-  if (rc != 0) return fail(LSTMP_B200_EUNSUPPORTED, "ncclAllReduce returned %d", rc);
+  h->nccl_comm = comm;
+  h->nccl_stream = (cudaStream_t)comm_stream;
+  h->exchange_pending = false;
   return 0;
 }
 

@@ -17,7 +17,7 @@ ABI_SYMBOLS = [
     "lstmp_b200_timing_enable", "lstmp_b200_timing_read", "lstmp_b200_debug_gemm",
     "lstmp_b200_xent_create", "lstmp_b200_xent_destroy", "lstmp_b200_xent_eval_masked",
     "lstmp_b200_xent_get_stats", "lstmp_b200_xent_reset_stats",
-    "lstmp_b200_update_clipped", "lstmp_b200_time_shift",
+    "lstmp_b200_update_clipped", "lstmp_b200_time_shift", "lstmp_b200_set_nccl",
     "lstmp_b200_dispatch_create", "lstmp_b200_dispatch_destroy", "lstmp_b200_dispatch_set_transform",
     "lstmp_b200_dispatch_load_utt", "lstmp_b200_dispatch_assemble", "lstmp_b200_dispatch_get_stats",
     "lstmp_b200_xent_eval_masked_logits",
@@ -93,6 +93,7 @@ def load_library():
     L.lstmp_b200_update.argtypes = [vp, fp, fp, vp]
     L.lstmp_b200_allreduce_grads_nccl.argtypes = [vp, vp, vp]
     L.lstmp_b200_update_clipped.argtypes = [vp, fp, fp, fp, vp]
+    L.lstmp_b200_set_nccl.argtypes = [vp, vp, vp]
     L.lstmp_b200_time_shift.argtypes = [vp, sz, vp, sz, ci, ci, ci, vp]
     L.lstmp_b200_get_info.argtypes = [vp, ctypes.POINTER(Info)]
     L.lstmp_b200_get_record.argtypes = [vp, ci, vp, sz, vp]
@@ -251,6 +252,11 @@ class Engine:
         """Update with the element-wise clip of the standard single-stream component (nnet-lstm-projected.h:480-493)."""
         _chk(load_library().lstmp_b200_update_clipped(self._h, float(learn_rate), float(momentum), float(max_grad),
                                                       self._stream()))
+
+    def set_nccl(self, comm_ptr, stream_ptr):
+        """Overlapped exchange inside backpropagate (lstmp_b200_set_nccl); comm_ptr None switches it off."""
+        _chk(load_library().lstmp_b200_set_nccl(self._h, ctypes.c_void_p(comm_ptr) if comm_ptr else None,
+                                                ctypes.c_void_p(stream_ptr) if stream_ptr else None))
 
     def allreduce_grads_nccl(self, comm_ptr, stream_ptr=None):
         """Sum all-reduce of the fresh-gradient arena over the raw ncclComm_t `comm_ptr` on `stream_ptr` (a

@@ -90,16 +90,28 @@ class NcclCommunicator:
 class GradientExchange:
     """Overlapped per-layer gradient all-reduce through the engine's C entry point on a side stream."""
 
-    def __init__(self, layers, device, group=None):
+    def __init__(self, layers, device, group=None, fused=True):
         self.layers = list(layers)
         self.device = torch.device(device)
         self.comm = NcclCommunicator(self.device, group)
         self.stream = torch.cuda.Stream(device=self.device)
         self._ready = [torch.cuda.Event() for _ in self.layers]   # layer k's gradient is final (compute stream)
         self._done = [torch.cuda.Event() for _ in self.layers]    # layer k's all-reduce finished (side stream)
+        # engines that can run the exchange themselves do it block by block INSIDE backpropagate (each gradient block is
+        # summed under the GEMMs that follow it, lstmp_b200_set_nccl) and wait for it in update; start / finish are
+        # then no-ops for that layer
+        self._fused = []
+        for layer in self.layers:
+            eng = layer.engine
+            ok = bool(fused) and hasattr(eng, "set_nccl")
+            if ok:
+                eng.set_nccl(self.comm.ptr, self.stream.cuda_stream)
+            self._fused.append(ok)
 
     def start(self, k):
         """Call right after layer k's Backpropagate was enqueued on the current stream."""
+        if self._fused[k]:
+            return
         self._ready[k].record(torch.cuda.current_stream(self.device))
         self.stream.wait_event(self._ready[k])
         self.layers[k].engine.allreduce_grads_nccl(self.comm.ptr, self.stream.cuda_stream)
@@ -107,9 +119,18 @@ class GradientExchange:
 
     def finish(self, k):
         """Call before layer k's Update(): the current stream waits for that layer's all-reduce only."""
+        if self._fused[k]:
+            return
         torch.cuda.current_stream(self.device).wait_event(self._done[k])
 
     def close(self):
+        for layer, f in zip(self.layers, self._fused):
+            if f:
+                try:
+                    layer.engine.set_nccl(None, None)
+                except Exception:
+                    pass
+        torch.cuda.synchronize(self.device)
         self.comm.close()
 
 
