@@ -535,7 +535,9 @@ static int gemm(lstmp_b200_handle_t h, int kind, float* C, long long ldc, int M,
                 cudaStream_t st, bool reuse_a = false) {
   Timed tm(h, kind, st);
 #ifdef LSTMP_HAVE_TC_GEMM
-  if (h->gemm_backend == 2) {
+  // (the per-timestep GEMMs of the weights-streamed mode, kinds 1 and 2, re-read the same weights every step: splitting
+  // them into tile images 2*T times per chunk costs more than it saves -- they stay on the 3xTF32 kernel)
+  if (h->gemm_backend == 2 && !(h->streamed && (kind == 1 || kind == 2))) {
     bool handled = false;
     int nl = 0;
     CUDA_TRY(launch_gemm_hl(&h->hlws, C, ldc, M, N, K, alpha, A, lda, tA, B, ldb, tB, beta, bias, st, &handled, h->gemm_ws,

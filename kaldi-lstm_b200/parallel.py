@@ -90,7 +90,7 @@ class NcclCommunicator:
 class GradientExchange:
     """Overlapped per-layer gradient all-reduce through the engine's C entry point on a side stream."""
 
-    def __init__(self, layers, device, group=None, fused=True):
+    def __init__(self, layers, device, group=None, fused=False):
         self.layers = list(layers)
         self.device = torch.device(device)
         self.comm = NcclCommunicator(self.device, group)
@@ -100,6 +100,13 @@ class GradientExchange:
         # engines that can run the exchange themselves do it block by block INSIDE backpropagate (each gradient block is
         # summed under the GEMMs that follow it, lstmp_b200_set_nccl) and wait for it in update; start / finish are
         # then no-ops for that layer
+        # fused=True (or LSTMP_B200_FUSED_EXCHANGE=1): block-wise exchange inside backpropagate.  Measured on 2 B200s
+        # (cfg3): 1.286 ms per step against 1.277 ms for one all-reduce per layer after its Backpropagate -- three
+        # smaller collectives cost more launch latency and SM contention with the gradient GEMMs than they hide -- so
+        # the per-layer exchange is the default (profiles/r2_exchange_ab.txt).
+        import os
+        if os.environ.get("LSTMP_B200_FUSED_EXCHANGE") is not None:
+            fused = os.environ["LSTMP_B200_FUSED_EXCHANGE"] != "0"
         self._fused = []
         for layer in self.layers:
             eng = layer.engine

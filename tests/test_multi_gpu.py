@@ -20,7 +20,7 @@ def _data():
     return xs, ods
 
 
-def _run(rank, world, port, q, c_path=False):
+def _run(rank, world, port, q, c_path=False, fused=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     import kaldi_lstm_b200 as klb
@@ -34,7 +34,8 @@ def _run(rank, world, port, q, c_path=False):
     comp.InitData("<CellDim> %d <NumStream> %d <ParamScale> 0.05" % (C, hi - lo), seed=3)
     comp.SetTrainOptions(klb.NnetTrainOptions(LR, MMT))
     # c_path: the engine's own entry point lstmp_b200_allreduce_grads_nccl on an own ncclComm_t and a side stream
-    exchange = klb.parallel.GradientExchange([comp], torch.device("cuda", rank)) if (c_path and world > 1) else None
+    exchange = (klb.parallel.GradientExchange([comp], torch.device("cuda", rank), fused=fused)
+                if (c_path and world > 1) else None)
     trainer = klb.parallel.StreamShardTrainer([comp], exchange=exchange)
     xs, ods = _data()
     for n in range(NCHUNK):
@@ -47,14 +48,16 @@ def _run(rank, world, port, q, c_path=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("c_path", [False, True])
+@pytest.mark.parametrize("c_path", [False, True, "fused"])
 def test_two_gpu_stream_sharding_matches_one_gpu(c_path):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, 2, 29650 + int(c_path), q, c_path)) for r in range(2)]
+    fused = c_path == "fused"   # block-wise exchange inside backpropagate (lstmp_b200_set_nccl)
+    procs = [ctx.Process(target=_run, args=(r, 2, 29650 + int(bool(c_path)) + int(fused), q, bool(c_path), fused))
+             for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in range(2))
