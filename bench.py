@@ -931,6 +931,34 @@ def main():
         except Exception as e:
             secondary["forward_only"] = {"error": str(e)[:200]}
 
+        # the loss of configs[3] at its per-GPU chunk (640 frames x 16624 pdfs): Xent::EvalMasked with sparse targets,
+        # and the fused softmax + xent of the output tail; device-resident net_out ring larger than L2
+        try:
+            xr, xP, xn = 640, 16624, 4
+            ys = [torch.softmax(torch.randn(xr, xP, device=dev) * 2, dim=1) for _ in range(xn)]
+            xdiff = torch.empty(xr, xP, device=dev)
+            xrng = np.random.RandomState(2)
+            xpost = (np.arange(xr + 1, dtype=np.int32), xrng.randint(0, xP, xr).astype(np.int32), np.ones(xr, np.float32))
+            xmask = (np.arange(xr) % 5 != 0).astype(np.float32)
+            xe = klb.Xent(xr, device=local_rank)
+            for i in range(5):
+                xe.EvalMasked(xmask, ys[i % xn], xpost, xdiff)
+            torch.cuda.synchronize()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            nx = 100
+            for i in range(nx):
+                xe.EvalMasked(xmask, ys[i % xn], xpost, xdiff)
+            x1.record()
+            torch.cuda.synchronize()
+            xms = x0.elapsed_time(x1) / nx
+            secondary["xent_cfg4"] = {"workload": "Xent::EvalMasked, 640 frames x 16624 pdfs, sparse hard targets, 1/5 masked "
+                                                  "(whole call: CSR H2D + 2 kernels)", "value": xr / (xms * 1e-3),
+                                      "unit": "frames/s", "us_per_call": 1e3 * xms,
+                                      "achieved_gbs": 8.0 * xr * xP / (xms * 1e-3) / 1e9, "alg_bytes": 8 * xr * xP}
+        except Exception as e:
+            secondary["xent_cfg4"] = {"error": str(e)[:200]}
+
     # ---- N > 1: the other configurations BASELINE.json names for 8 GPUs, device-resident, same timing rules --------
     if world > 1 and not args.no_secondary:
         def measure_stack(shapes, S2, T2, nsteps):

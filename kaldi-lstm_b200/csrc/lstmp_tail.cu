@@ -40,21 +40,30 @@ cudaError_t launch_gemm_tc(float* C, long long ldc, int M, int N, int K, float a
                            cudaStream_t stream, bool* handled, float* ws, size_t ws_floats, int* nlaunch);
 #endif
 
-// g[c] = sum over rows of diff[r][c] in a fixed order (AddRowSumMat): one thread per column, coalesced across columns
+// g[c] = sum over rows of diff[r][c] in a fixed order (AddRowSumMat).  32 columns x 8 row lanes per CTA: a warp reads
+// 128 contiguous bytes of a row, lane j of a column sums rows j, j+8, ... and the 8 partials are added in order.
 __global__ void __launch_bounds__(256) colsum_kernel(float* __restrict__ g, const float* __restrict__ diff, long long ld,
                                                      int rows, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int r = 0;
-  for (; r + 3 < rows; r += 4) {
-    a0 += diff[(long long)r * ld + c];
-    a1 += diff[(long long)(r + 1) * ld + c];
-    a2 += diff[(long long)(r + 2) * ld + c];
-    a3 += diff[(long long)(r + 3) * ld + c];
+  __shared__ float part[8][33];
+  const int cx = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < cols) {
+    int r = j;
+    for (; r + 8 < rows; r += 16) {
+      a0 += diff[(long long)r * ld + c];
+      a1 += diff[(long long)(r + 8) * ld + c];
+    }
+    if (r < rows) a0 += diff[(long long)r * ld + c];
   }
-  for (; r < rows; ++r) a0 += diff[(long long)r * ld + c];
-  g[c] = (a0 + a1) + (a2 + a3);
+  part[j][cx] = a0 + a1;
+  __syncthreads();
+  if (j == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][cx];
+    g[c] = t;
+  }
 }
 }  // namespace lstmp
 
@@ -247,7 +256,7 @@ extern "C" int lstmp_b200_tail_backpropagate(lstmp_b200_tail_handle_t h, const f
   // G(W) = diff^T * in ; G(b) = column sums of diff                        (AffineTransform::Update, gradient part)
   if ((rc = tail_gemm(h, h->grads, h->I, h->P, h->I, num_frames, h->diff, h->P, 1, in, (long long)ld_in, 0, nullptr, st)))
     return rc;
-  colsum_kernel<<<(h->P + 255) / 256, 256, 0, st>>>(h->grads + (size_t)h->P * h->I, h->diff, h->P, num_frames, h->P);
+  colsum_kernel<<<(h->P + 31) / 32, 256, 0, st>>>(h->grads + (size_t)h->P * h->I, h->diff, h->P, num_frames, h->P);
   T_TRY(cudaGetLastError());
   h->launches++;
   return 0;
