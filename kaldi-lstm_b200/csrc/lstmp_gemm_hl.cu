@@ -32,7 +32,9 @@ constexpr uint32_t TILE = 128 * 128;                 // bytes of one [128 rows x
 constexpr int NSTAGE = 3;                            // stages of A_hi | A_lo | B_hi | B_lo = 64 KB
 constexpr uint32_t STAGE = 4 * TILE;
 constexpr int THREADS = 192;                         // warp 0 producer, warp 1 MMA issuer + TMEM, warps 2-5 epilogue
-constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 + 256;
+constexpr int PLD = 36;                              // row stride (floats) of an epilogue warp's [32 x 32] staging patch
+constexpr uint32_t PATCH = 32 * PLD * 4;
+constexpr uint32_t SMEM = NSTAGE * STAGE + 4 * PATCH + 1024 + 256;
 
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
@@ -143,41 +145,42 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t 
       : "memory");
 }
 
-// grid = (N tiles, M tiles, K splits).  a_img / b_img: tile images of op(A) [M x K] and op(B)^T [N x K].
+// PERSISTENT: grid = min(work items, #SMs) CTAs; work item w = (m tile, n tile, K split), m fastest (the CTAs that run
+// at the same time share the B tile in L2), item w of CTA c = c + i * gridDim.x.  The accumulator is double-buffered in
+// TMEM (2 x 128 columns): the four epilogue warps drain tile i (tcgen05.ld -> alpha/beta/bias -> 64 contiguous bytes
+// per lane and load) while the producer / MMA warps are already in the main loop of tile i+1; the shared-memory ring
+// runs continuously across tiles.  a_img / b_img: tile images of op(A) [M x K] and op(B)^T [N x K].
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_hl_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int nkt, float alpha, const uint8_t* __restrict__ a_img,
-               const uint8_t* __restrict__ b_img, float beta, const float* __restrict__ bias, int kt_per_split,
-               float* __restrict__ split_ws) {
+gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nkt, float alpha_in,
+               const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, float beta_in,
+               const float* __restrict__ bias_in, int kt_per_split, int splits, float* __restrict__ split_ws) {
   extern __shared__ __align__(128) uint8_t smem_raw_hl[];
   uint8_t* tiles = smem_raw_hl + ((1024u - (smem_u32(smem_raw_hl) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * STAGE);
+  float* patches = reinterpret_cast<float*>(tiles + NSTAGE * STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * STAGE + 4 * PATCH);
   uint64_t* empty = full + NSTAGE;
-  uint64_t* accum_ready = empty + NSTAGE;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
+  uint64_t* acc_full = empty + NSTAGE;   // [2] accumulator buffer complete (MMA warp -> epilogue)
+  uint64_t* acc_empty = acc_full + 2;    // [2] accumulator buffer drained (4 epilogue warps -> MMA warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  int kt0 = 0, nk = nkt;
-  if (split_ws) {  // split-K: raw partial sums to split_ws[z][M x N]; splitk_reduce applies alpha / beta / bias
-    kt0 = blockIdx.z * kt_per_split;
-    nk = min(kt_per_split, nkt - kt0);
-    Cm = split_ws + (size_t)blockIdx.z * M * N;
-    ldc = N;
-    alpha = 1.f;
-    beta = 0.f;
-    bias = nullptr;
-  }
+  const int ntm = (M + BM - 1) / BM, ntn = (N + BN - 1) / BN;
+  const int nitems = ntm * ntn * splits;
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_ready, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(BN)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "n"(2 * BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -188,110 +191,144 @@ gemm_hl_kernel(float* __restrict__ Cm, long long ldc, int M, int N, int nkt, flo
   const uint32_t tiles_s = smem_u32(tiles);
 
   if (warp == 0) {
-    // ------------------------------ producer: 4 bulk copies per K block ----------------------
+    // ------------------------------ producer: 2 bulk copies of 32 KB per K block -------------
     if (lane == 0) {
-      const uint8_t* ap = a_img + ((size_t)blockIdx.y * nkt + kt0) * 2 * TILE;   // A_hi | A_lo of (mt, kt) are adjacent
-      const uint8_t* bp = b_img + ((size_t)blockIdx.x * nkt + kt0) * 2 * TILE;
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % NSTAGE;
-        if (kb >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kb / NSTAGE) - 1) & 1));
-        mbar_arrive_expect_tx(&full[s], STAGE);
-        const uint32_t dst = tiles_s + s * STAGE;
-        bulk_g2s(dst, ap + (size_t)kb * 2 * TILE, 2 * TILE, &full[s]);
-        bulk_g2s(dst + 2 * TILE, bp + (size_t)kb * 2 * TILE, 2 * TILE, &full[s]);
+      uint32_t kbc = 0;  // K blocks issued so far (ring position, continuous across work items)
+      for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+        const int mt = w % ntm, nt = (w / ntm) % ntn, z = w / (ntm * ntn);
+        const int kt0 = z * kt_per_split, nk = min(kt_per_split, nkt - kt0);
+        const uint8_t* ap = a_img + ((size_t)mt * nkt + kt0) * 2 * TILE;   // A_hi | A_lo of (mt, kt) are adjacent
+        const uint8_t* bp = b_img + ((size_t)nt * nkt + kt0) * 2 * TILE;
+        for (int kb = 0; kb < nk; ++kb, ++kbc) {
+          const uint32_t s = kbc % NSTAGE, u = kbc / NSTAGE;
+          if (u > 0) mbar_wait(&empty[s], (u - 1) & 1);
+          mbar_arrive_expect_tx(&full[s], STAGE);
+          const uint32_t dst = tiles_s + s * STAGE;
+          bulk_g2s(dst, ap + (size_t)kb * 2 * TILE, 2 * TILE, &full[s]);
+          bulk_g2s(dst + 2 * TILE, bp + (size_t)kb * 2 * TILE, 2 * TILE, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer -----------------------------------------------
     // kind::f16, bf16 x bf16 -> fp32, both operands K-major: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % NSTAGE;
-      mbar_wait(&full[s], (uint32_t)((kb / NSTAGE) & 1));
-      tc::tc_fence_after();
-      {
-        const uint32_t a_hi = tiles_s + s * STAGE, a_lo = a_hi + TILE, b_hi = a_hi + 2 * TILE, b_lo = b_hi + TILE;
-#pragma unroll
-        for (int j = 0; j < BK / 16; ++j) {
-          const uint64_t dah = tc::make_desc_sw128(a_hi + 32 * j), dal = tc::make_desc_sw128(a_lo + 32 * j);
-          const uint64_t dbh = tc::make_desc_sw128(b_hi + 32 * j), dbl = tc::make_desc_sw128(b_lo + 32 * j);
-          if (tc::elect_one()) mma_bf16(tmem_base, dal, dbl, idesc, (kb | j) ? 1u : 0u);  // small terms first
-          if (tc::elect_one()) mma_bf16(tmem_base, dal, dbh, idesc, 1u);
-          if (tc::elect_one()) mma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          if (tc::elect_one()) mma_bf16(tmem_base, dah, dbh, idesc, 1u);
-        }
-        if (tc::elect_one()) {
-          tc::umma_commit(&empty[s]);
-          if (kb == nk - 1) tc::umma_commit(accum_ready);
-        }
+    uint32_t kbc = 0, it = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
+      const int z = w / (ntm * ntn);
+      const int kt0 = z * kt_per_split, nk = min(kt_per_split, nkt - kt0);
+      const uint32_t buf = it & 1, ub = it >> 1;
+      if (ub > 0) {  // the epilogue has drained this accumulator buffer (its previous tile)
+        mbar_wait(&acc_empty[buf], (ub - 1) & 1);
+        tc::tc_fence_after();
       }
-      __syncwarp();
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      for (int kb = 0; kb < nk; ++kb, ++kbc) {
+        const uint32_t s = kbc % NSTAGE, u = kbc / NSTAGE;
+        mbar_wait(&full[s], u & 1);
+        tc::tc_fence_after();
+        {
+          const uint32_t a_hi = tiles_s + s * STAGE, a_lo = a_hi + TILE, b_hi = a_hi + 2 * TILE, b_lo = b_hi + TILE;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {
+            const uint64_t dah = tc::make_desc_sw128(a_hi + 32 * j), dal = tc::make_desc_sw128(a_lo + 32 * j);
+            const uint64_t dbh = tc::make_desc_sw128(b_hi + 32 * j), dbl = tc::make_desc_sw128(b_lo + 32 * j);
+            if (tc::elect_one()) mma_bf16(tmem_d, dal, dbl, idesc, (kb | j) ? 1u : 0u);  // small terms first
+            if (tc::elect_one()) mma_bf16(tmem_d, dal, dbh, idesc, 1u);
+            if (tc::elect_one()) mma_bf16(tmem_d, dah, dbl, idesc, 1u);
+            if (tc::elect_one()) mma_bf16(tmem_d, dah, dbh, idesc, 1u);
+          }
+          if (tc::elect_one()) {
+            tc::umma_commit(&empty[s]);
+            if (kb == nk - 1) tc::umma_commit(&acc_full[buf]);
+          }
+        }
+        __syncwarp();
+      }
     }
     tc::tc_fence_before();
   } else {
     // ------------------------------ epilogue (warps 2-5: TMEM lane quadrants 2, 3, 0, 1) -----
-    // TMEM -> shared memory (the operand ring is idle once the last MMA has committed) -> global memory with whole
-    // rows per warp: 512 contiguous bytes per store instruction instead of 32 scattered 16-byte pieces.
-    constexpr int LDT = BN + 4;  // padded row stride (floats): conflict-free 128-bit stores of a TMEM lane's row
-    float* stage_t = reinterpret_cast<float*>(tiles);
-    if (nk > 0) {
-      mbar_wait(accum_ready, 0);
-      tc::tc_fence_after();
-    }
     const int quad = warp & 3;
-    {
-      float* srow = stage_t + (size_t)(quad * 32 + lane) * LDT;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        float v[16];
-        if (nk > 0) {
-          tc::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(srow + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
+      const int mt = w % ntm, nt = (w / ntm) % ntn, z = w / (ntm * ntn);
+      const int m0 = mt * BM, n0 = nt * BN;
+      float* Cm = Cout;
+      long long ldc = ldc_out;
+      float alpha = alpha_in, beta = beta_in;
+      const float* bias = bias_in;
+      if (split_ws) {  // split-K: raw partial sums to split_ws[z][M x N]; splitk_reduce applies alpha / beta / bias
+        Cm = split_ws + (size_t)z * M * N;
+        ldc = N;
+        alpha = 1.f;
+        beta = 0.f;
+        bias = nullptr;
       }
-    }
-    __syncwarp();  // each warp re-reads only the 32 rows it wrote itself
-    const int gn = n0 + 4 * lane;
-    const bool vec_ok = ((ldc & 3) == 0) && gn + 3 < N;
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias && vec_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + gn));
-#pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-      const int gm = m0 + quad * 32 + rr;
-      if (gm >= M) break;
-      const float4 a4 = *reinterpret_cast<const float4*>(stage_t + (size_t)(quad * 32 + rr) * LDT + 4 * lane);
-      float* crow = Cm + (size_t)gm * ldc;
-      if (vec_ok) {
-        float4 o = make_float4(alpha * a4.x, alpha * a4.y, alpha * a4.z, alpha * a4.w);
-        if (beta != 0.f) {
-          const float4 cc = *reinterpret_cast<const float4*>(crow + gn);
-          o.x += beta * cc.x; o.y += beta * cc.y; o.z += beta * cc.z; o.w += beta * cc.w;
-        }
-        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-        *reinterpret_cast<float4*>(crow + gn) = o;
-      } else {
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      const uint32_t buf = it & 1, ub = it >> 1;
+      mbar_wait(&acc_full[buf], ub & 1);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16);
+      float* patch = patches + (size_t)(warp - 2) * (PATCH / 4);
+      // 32 columns at a time: TMEM lane (= row) -> this warp's staging patch -> global memory with 8 lanes per row,
+      // i.e. whole 128-byte lines per store instruction (4 rows each) instead of 32 scattered 16-byte pieces
+      const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[16], v2[16];
+        tc::tmem_ld16(taddr + (uint32_t)c, v);
+        tc::tmem_ld16(taddr + (uint32_t)(c + 16), v2);
+        float* prow = patch + lane * PLD;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (gn + q < N) {
-            float o = alpha * av[q];
-            if (beta != 0.f) o += beta * crow[gn + q];
-            if (bias) o += bias[gn + q];
-            crow[gn + q] = o;
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(prow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          *reinterpret_cast<float4*>(prow + 16 + j) = make_float4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
+        }
+        __syncwarp();
+        const int gn = n0 + c + c4;
+        const bool vec_ok = ((ldc & 3) == 0) && gn + 3 < N;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && vec_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + gn));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = rsub + 4 * i;
+          const int gm = m0 + quad * 32 + rl;
+          if (gm < M) {
+            const float4 a4 = *reinterpret_cast<const float4*>(patch + rl * PLD + c4);
+            float* crow = Cm + (size_t)gm * ldc;
+            if (vec_ok) {
+              float4 o = make_float4(alpha * a4.x, alpha * a4.y, alpha * a4.z, alpha * a4.w);
+              if (beta != 0.f) {
+                const float4 cc = *reinterpret_cast<const float4*>(crow + gn);
+                o.x += beta * cc.x; o.y += beta * cc.y; o.z += beta * cc.z; o.w += beta * cc.w;
+              }
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              *reinterpret_cast<float4*>(crow + gn) = o;
+            } else {
+              const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (gn + q < N) {
+                  float o = alpha * av[q];
+                  if (beta != 0.f) o += beta * crow[gn + q];
+                  if (bias) o += bias[gn + q];
+                  crow[gn + q] = o;
+                }
+              }
+            }
           }
         }
+        __syncwarp();  // the patch is rewritten in the next iteration
       }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);  // this warp's quadrant of the buffer is free again
     }
-    tc::tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 }  // namespace hl
@@ -333,30 +370,35 @@ cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alph
     attr_set[dev & 63] = true;
   }
   const int nkt = (K + hl::BK - 1) / hl::BK;
-  dim3 grid((N + hl::BN - 1) / hl::BN, (M + hl::BM - 1) / hl::BM), block(hl::THREADS);
-  const int tiles = grid.x * grid.y;
+  const int ntm = (M + hl::BM - 1) / hl::BM, ntn = (N + hl::BN - 1) / hl::BN;
+  const int tiles = ntm * ntn;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   int splits = 1;
-  // split-K when the output tiles alone cannot fill the 148 SMs (in_diff: 40 tiles, G(w_r_m): 28 tiles)
+  // split-K when the output tiles alone cannot fill the SMs (in_diff: 40 tiles, G(w_r_m): 28 tiles)
   if (ws && tiles < 100 && nkt >= 4 && (N & 3) == 0) {
-    splits = 148 / tiles;
+    splits = nsm / tiles;
     if (splits > 8) splits = 8;
     if (splits > nkt / 2) splits = nkt / 2;
     while (splits > 1 && (size_t)splits * M * N > ws_floats) --splits;
   }
+  int kts = nkt;
   if (splits > 1) {
-    const int kts = (nkt + splits - 1) / splits;
+    kts = (nkt + splits - 1) / splits;
     splits = (nkt + kts - 1) / kts;
-    grid.z = splits;
-    hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(C, ldc, M, N, nkt, alpha, a_img, b_img, beta, bias, kts, ws);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+  }
+  const int items = tiles * splits;
+  dim3 grid(items < nsm ? items : nsm), block(hl::THREADS);
+  hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(C, ldc, M, N, nkt, alpha, a_img, b_img, beta, bias, kts, splits,
+                                                        splits > 1 ? ws : nullptr);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (splits > 1) {
     *nlaunch = 2;
     return launch_splitk_reduce(C, ldc, M, N, alpha, beta, bias, ws, splits, stream);
   }
-  hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(C, ldc, M, N, nkt, alpha, a_img, b_img, beta, bias, nkt, nullptr);
-  return cudaGetLastError();
+  return cudaSuccess;
 }
-
 
 // One call = split both operands (unless the caller says op(A)'s image of the previous call is still valid), run the
 // GEMM.  The image buffers grow on demand and belong to the caller's handle (one stream at a time per handle).
