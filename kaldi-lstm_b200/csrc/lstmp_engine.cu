@@ -284,19 +284,23 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
       // stream groups: each group gathers only its own streams' activations (half the L2 -> SM traffic per CTA with
       // two groups) at the price of twice the weight slice per CTA; the largest count whose slices fit, >= 16 streams
       const int gforce = env_int("LSTMP_B200_TMA_GROUPS", 0);
+      // the backward kernel may use its own group count (LSTMP_B200_TMA_GROUPS_BWD): its shared memory holds two
+      // weight slices, so fewer groups (smaller slices) leave it a deeper operand ring
+      const int gforce_b = env_int("LSTMP_B200_TMA_GROUPS_BWD", 0);
       for (int G = gforce > 0 ? gforce : 2; G >= 1 && !h->rec_tma; G = (gforce > 0 ? 0 : G - 1)) {
         if (G > 2 || S % G || (G > 1 && gforce <= 0 && S / G < 16)) continue;  // barrier counters for <= 2 groups
+        const int Gb = (gforce_b > 0 && gforce_b <= 2 && S % gforce_b == 0) ? gforce_b : G;
         FwdTmaParams f{};
         BwdTmaParams b{};
         size_t fs = 0, bs = 0;
         bool okt = fwd_tma_plan(C, R, S, G, sm_use, smem_limit, &f, &fs);
         // the backward grid is the largest co-resident set of kp-CTA clusters; its shared-memory size depends on the
         // grid through the slice sizes, so plan with the optimistic grid first and again with the real one
-        if (okt) okt = bwd_tma_plan(C, R, S, G, sm_use, kp, smem_limit, &b, &bs);
+        if (okt) okt = bwd_tma_plan(C, R, S, Gb, sm_use, kp, smem_limit, &b, &bs);
         if (okt) okt = tma_set_smem_limits(fs, bs) == cudaSuccess;
         if (okt) {
           const int n = bwd_tma_max_ctas(kp, bs, sm_use);
-          okt = n >= kp * G && bwd_tma_plan(C, R, S, G, n, kp, smem_limit, &b, &bs) &&
+          okt = n >= kp * Gb && bwd_tma_plan(C, R, S, Gb, n, kp, smem_limit, &b, &bs) &&
                 tma_set_smem_limits(fs, bs) == cudaSuccess && bwd_tma_max_ctas(kp, bs, sm_use) >= b.nctas;
         }
         if (okt) {
@@ -350,8 +354,9 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
     // exchange arrays: per group and 64-k chunk one tile image of roundup8(2*Sg) rows x 128 bytes; zero-initialised so
     // that the k tail of the last chunk (never written) contributes nothing
     const size_t tile = (size_t)((2 * h->ftm.Sg + 7) & ~7) * 128, G = (size_t)h->ftm.G;
-    const size_t n_r = G * h->ftm.nch_g * tile, n_m = G * h->ftm.nch_p * tile, n_dg = G * h->btm.nch_a * tile,
-                 n_dr = G * h->btm.nch_b * tile;
+    const size_t tile_b = (size_t)((2 * h->btm.Sg + 7) & ~7) * 128, Gb = (size_t)h->btm.G;
+    const size_t n_r = G * h->ftm.nch_g * tile, n_m = G * h->ftm.nch_p * tile, n_dg = Gb * h->btm.nch_a * tile_b,
+                 n_dr = Gb * h->btm.nch_b * tile_b;
     const size_t total = n_r + n_m + n_dg + n_dr;
     e = cudaMalloc((void**)&h->rhl, total);
     if (e == cudaSuccess) e = cudaMemset(h->rhl, 0, total);

@@ -117,3 +117,16 @@ def test_tail_error_behaviour(klb):
         tail.PropagateEval(x, np.ones(8, np.float32), [[(40, 1.0)]] * 8)
     with pytest.raises(RuntimeError):
         tail.InitData("<ParamStdev> 0.1")
+
+
+def test_cpp_tail_mirror_on_gpu():
+    """kaldi-lstm_b200/kaldi/b200-affine-softmax-xent.h (B200AffineSoftmaxXent: PropagateEval / Backpropagate / Update /
+    Report against Kaldi's types) vs a double-precision host restatement (tests/cpp/tail_test.cc)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "tests", "cpp"), "-s"])
+    r = subprocess.run([os.path.join(root, "tests", "cpp", "_build", "tail_test")], capture_output=True, text=True,
+                       timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
