@@ -3,7 +3,7 @@
 
   ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_rN.csv \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
-  ncu --set full --clock-control none --import-source on -k regex:"lstmp_.*_kernel|gemm_tc_kernel" -s 14 -c 12 \
+  ncu --set full --clock-control none --import-source on -k regex:"lstmp_.*_kernel|gemm_hl_kernel|split_hl" -s 20 -c 24 \
       -o gpurun_out/prof_rN python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
 
 usage: tools/make_profiles.py <round> [launches.csv] [prof.ncu-rep]
@@ -96,8 +96,8 @@ def full_selected(rnd, rep):
     acc = collections.defaultdict(list)
     for r in data:
         name = r[col["Kernel Name"]]
-        key = ("fwd_recurrent" if ("lstmp_fwd_kernel" in name or "lstmp_fwd_tc_kernel" in name) else "bwd_recurrent" if "lstmp_bwd_kernel" in name
-               else "gemm_tc" if "gemm_tc_kernel" in name else None)
+        key = ("fwd_recurrent" if "lstmp_fwd_" in name else "bwd_recurrent" if "lstmp_bwd_" in name
+               else "gemm" if ("gemm_hl_kernel" in name or "gemm_tc_kernel" in name) else None)
         if key is None:
             continue
         acc[key].append(tobytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) +
