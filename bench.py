@@ -438,6 +438,8 @@ def bench_cfg4(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("LSTMP_B200_BENCH_NCCL_ALGO", "Ring") != "none":
+            os.environ.setdefault("NCCL_ALGO", os.environ.get("LSTMP_B200_BENCH_NCCL_ALGO", "Ring"))
         dist.init_process_group("nccl", device_id=dev)
     lstm = klb.LstmProjectedStreams(I0, R, device=local_rank, max_frames=T)
     lstm.InitData("<CellDim> %d <NumStream> %d <ParamScale> %g" % (C, S, PARAM_SCALE), seed=4321)
@@ -642,6 +644,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the gradient all-reduces are 9-34 MB: on 8 B200s NCCL's default choice measured 1.327 ms per step, the ring
+        # algorithm 1.289 ms (profiles/r2_nccl_algo_n8.txt); NCCL_ALGO set by the user wins
+        if os.environ.get("LSTMP_B200_BENCH_NCCL_ALGO", "Ring") != "none":
+            os.environ.setdefault("NCCL_ALGO", os.environ.get("LSTMP_B200_BENCH_NCCL_ALGO", "Ring"))
         dist.init_process_group("nccl", device_id=dev)
     S, T = wl["S"], wl["T"]
     rows = S * T
