@@ -104,7 +104,7 @@ struct BwdTmaParams {
   int gt;                       // 64-k tiles per ring slot = per bulk copy
   unsigned slot_bytes;
   unsigned chunk_a, chunk_b;
-  unsigned off_ba, off_bb, off_ring, off_red, ldred, off_dgn, off_dcn, off_acc7, off_peep, off_bars;
+  unsigned off_ba, off_bb, off_ring, off_red, ldred, off_ext, off_peep, off_bars;
   const float *w_gifo_r, *w_r_m, *p_i, *p_f, *p_o;
   const float *gifo, *cbuf, *hbuf;
   const float* out_diff;

@@ -536,10 +536,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
   uint8_t* base = smem_raw_tma + ((1024u - (smem_u32(smem_raw_tma) & 1023u)) & 1023u);
   uint8_t* ba = base + p.off_ba;  // W_gifo_r[my K slice, my cluster's r columns]^T: tiles [roundup8(2*rpb) rows][128 B]
   uint8_t* bb = base + p.off_bb;  // W_r_m[:, my cells]^T: nch_b tiles of [roundup8(2*cpc) rows][128 B]
-  float* red = reinterpret_cast<float*>(base + p.off_red);    // [128][ldred]  (phase A: read by the whole cluster)
-  float* dgn = reinterpret_cast<float*>(base + p.off_dgn);    // [2][Sg*cpc]: d_i(t+1), d_f(t+1) of my cells
-  float* dcn = reinterpret_cast<float*>(base + p.off_dcn);    // [Sg*cpc]    d_c(t+1)
-  float* acc7 = reinterpret_cast<float*>(base + p.off_acc7);  // [Sg*cpc][7] running sums for bias / peephole gradients
+  float* red = reinterpret_cast<float*>(base + p.off_red);    // [roundup32(2*Sg)][ldred]  (phase A: read by the cluster)
+  // Per-element state carried from step to step -- d_i(t+1), d_f(t+1), d_c(t+1) and the seven running sums of the
+  // bias / peephole gradients -- lives in REGISTERS for a thread's first two elements (element idx = tid + rd * 384:
+  // the same thread owns it in every timestep); only elements beyond 2 * 384 per CTA (few-CTA runs) use this buffer.
+  // That frees ~17 KB of shared memory for a third ring slot at cfg3.
+  float* ext = reinterpret_cast<float*>(base + p.off_ext);    // [max(0, Sg*cpc - 2*384)][10]
   float* peep = reinterpret_cast<float*>(base + p.off_peep);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + p.off_bars);
   Ring rg;
@@ -620,9 +622,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       split8_store(v, t + tc::sw128_off(n, k8 & 7), t + tc::sw128_off(cpc + n, k8 & 7));
     }
   }
-  for (int idx = tid; idx < 2 * Sg * cpc; idx += kThreads) dgn[idx] = 0.f;  // row-block T+1 is zero (LPS.h:352)
-  for (int idx = tid; idx < Sg * cpc; idx += kThreads) dcn[idx] = 0.f;
-  for (int idx = tid; idx < Sg * cpc * 7; idx += kThreads) acc7[idx] = 0.f;
+  float st0[10], st1[10];  // [0] d_i(t+1), [1] d_f(t+1), [2] d_c(t+1) (row-block T+1 is zero, LPS.h:352), [3..9] sums
+#pragma unroll
+  for (int q = 0; q < 10; ++q) st0[q] = st1[q] = 0.f;
+  for (int idx = tid; idx < (Sg * cpc - 2 * kThreads) * 10; idx += kThreads) ext[idx] = 0.f;
   for (int cl = tid; cl < nc; cl += kThreads) {
     peep[cl] = p.p_i[c0 + cl];
     peep[cpc + cl] = p.p_f[c0 + cl];
@@ -669,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
                       tmem_base + COL_A, rpb, nn, red, ldred);
         } else {
           if (is_sync_thread()) gs.wait();
-          for (int idx = tid; idx < 128 * ldred; idx += kThreads) red[idx] = 0.f;
+          for (int idx = tid; idx < ((2 * Sg + 31) & ~31) * ldred; idx += kThreads) red[idx] = 0.f;
         }
         stamp(41);
         cluster_sync_all();  // the kp partial blocks of this cluster are complete
@@ -726,53 +729,57 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
       tma_product<GT>(ps, rg, gs, true, drhl, Sg, 0, p.nch_b, rot_b, bb_s, p.chunk_b, idesc_b,
                   tmem_base + COL_B, cpc, nc, red, ldred);
       stamp(45);
-      for (int idx = tid; idx < Sg * nc; idx += kThreads) {
-        int s = idx / nc, cl = idx - s * nc;
-        size_t row = (size_t)tt * S + s_base + s;
-        float yg, yi, yf, yo, yc, ycp, yh, yfn;
-        if (idx < 2 * kThreads) {
-          const int rd = idx >= kThreads ? 1 : 0;
-          yg = rd ? yv[1][0] : yv[0][0]; yi = rd ? yv[1][1] : yv[0][1]; yf = rd ? yv[1][2] : yv[0][2];
-          yo = rd ? yv[1][3] : yv[0][3]; yc = rd ? yv[1][4] : yv[0][4]; ycp = rd ? yv[1][5] : yv[0][5];
-          yh = rd ? yv[1][6] : yv[0][6]; yfn = rd ? yv[1][7] : yv[0][7];
-        } else {
-          const float* gp = p.gifo + row * (4 * C) + c0 + cl;
-          yg = gp[0]; yi = gp[C]; yf = gp[2 * C]; yo = gp[3 * C];
-          yc = p.cbuf[(row + S) * C + c0 + cl];
-          ycp = p.cbuf[row * C + c0 + cl];  // c(t-1): block tt
-          yh = p.hbuf[row * C + c0 + cl];
-          yfn = have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f;  // f(t+1)
-        }
-        float pi = peep[cl], pf = peep[cpc + cl], po = peep[2 * cpc + cl];
-        float d_m = red[s * ldred + cl] + red[(Sg + s) * ldred + cl];
-        float d_h = (d_m * yo) * (1.0f - yh * yh);            // :411-412
-        float d_o = (d_m * yh) * yo * (1.0f - yo);            // :415-416
+      const int n_el = Sg * nc;
+      // one element (stream s, cell cl): y = its activation record, st = its carried state
+      auto element = [&](int idx, const float (&y)[8], float (&st)[10]) {
+        const int s = idx / nc, cl = idx - s * nc;
+        const float yg = y[0], yi = y[1], yf = y[2], yo = y[3], yc = y[4], ycp = y[5], yh = y[6], yfn = y[7];
+        const float pi = peep[cl], pf = peep[cpc + cl], po = peep[2 * cpc + cl];
+        const float d_m = red[s * ldred + cl] + red[(Sg + s) * ldred + cl];
+        const float d_h = (d_m * yo) * (1.0f - yh * yh);      // :411-412
+        const float d_o = (d_m * yh) * yo * (1.0f - yo);      // :415-416
         float d_c = d_h;                                      // :424
-        d_c += dcn[idx] * yfn;                                // :425
-        d_c += dgn[idx] * pi;                                 // :426
-        d_c += dgn[Sg * cpc + idx] * pf;                      // :427
+        d_c += st[2] * yfn;                                   // :425
+        d_c += st[0] * pi;                                    // :426
+        d_c += st[1] * pf;                                    // :427
         d_c += d_o * po;                                      // :428
-        float d_f = (d_c * ycp) * yf * (1.0f - yf);           // :431-432
-        float d_i = (d_c * yg) * yi * (1.0f - yi);            // :435-436
-        float d_g = (d_c * yi) * (1.0f - yg * yg);            // :439-440
+        const float d_f = (d_c * ycp) * yf * (1.0f - yf);     // :431-432
+        const float d_i = (d_c * yg) * yi * (1.0f - yi);      // :435-436
+        const float d_g = (d_c * yi) * (1.0f - yg * yg);      // :439-440
         // DGIFO(t) hi/lo is what the other CTAs wait for; the fp32 record is stored after the arrive
         store_hl(dghl, Sg, tile_bytes, s, c0 + cl, d_g);
         store_hl(dghl, Sg, tile_bytes, s, C + c0 + cl, d_i);
         store_hl(dghl, Sg, tile_bytes, s, 2 * C + c0 + cl, d_f);
         store_hl(dghl, Sg, tile_bytes, s, 3 * C + c0 + cl, d_o);
-        dgn[idx] = d_i;
-        dgn[Sg * cpc + idx] = d_f;
-        dcn[idx] = d_c;
-        red[s * ldred + cl] = d_g;         // parked for pass 2 (d_i, d_f are in dgn)
+        st[0] = d_i;
+        st[1] = d_f;
+        st[2] = d_c;
+        red[s * ldred + cl] = d_g;         // parked for pass 2 (d_i, d_f are in the carried state)
         red[(Sg + s) * ldred + cl] = d_o;
-        float* a7 = acc7 + (size_t)idx * 7;
-        a7[0] += d_g;          // bias_corr_ column sums (:474)
-        a7[1] += d_i;
-        a7[2] += d_f;
-        a7[3] += d_o;
-        a7[4] += d_i * ycp;    // peephole_i_c_corr_  DI(t) .* C(t-1)  (:477)
-        a7[5] += d_f * ycp;    // peephole_f_c_corr_                  (:480)
-        a7[6] += d_o * yc;     // peephole_o_c_corr_  DO(t) .* C(t)    (:483)
+        st[3] += d_g;          // bias_corr_ column sums (:474)
+        st[4] += d_i;
+        st[5] += d_f;
+        st[6] += d_o;
+        st[7] += d_i * ycp;    // peephole_i_c_corr_  DI(t) .* C(t-1)  (:477)
+        st[8] += d_f * ycp;    // peephole_f_c_corr_                  (:480)
+        st[9] += d_o * yc;     // peephole_o_c_corr_  DO(t) .* C(t)    (:483)
+      };
+      if (tid < n_el) element(tid, yv[0], st0);
+      if (tid + kThreads < n_el) element(tid + kThreads, yv[1], st1);
+      for (int idx = tid + 2 * kThreads; idx < n_el; idx += kThreads) {
+        const int s = idx / nc, cl = idx - s * nc;
+        const size_t row = (size_t)tt * S + s_base + s;
+        const float* gp = p.gifo + row * (4 * C) + c0 + cl;
+        const float y[8] = {gp[0], gp[C], gp[2 * C], gp[3 * C], p.cbuf[(row + S) * C + c0 + cl],
+                            p.cbuf[row * C + c0 + cl] /* c(t-1): block tt */, p.hbuf[row * C + c0 + cl],
+                            have_next ? gp[(size_t)S * 4 * C + 2 * C] : 0.f /* f(t+1) */};
+        float* e = ext + (size_t)(idx - 2 * kThreads) * 10;
+        float st[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) st[q] = e[q];
+        element(idx, y, st);
+#pragma unroll
+        for (int q = 0; q < 10; ++q) e[q] = st[q];
       }
       fence_async_global();
     } else {
@@ -786,9 +793,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
         int s = idx / nc, cl = idx - s * nc;
         size_t row = (size_t)tt * S + s_base + s;
         float* dp = p.dgifo + row * (4 * C) + c0 + cl;
+        const float* e = ext + (size_t)(idx - 2 * kThreads) * 10;  // (only dereferenced for idx >= 2 * 384)
         dp[0] = red[s * ldred + cl];
-        dp[C] = dgn[idx];
-        dp[2 * C] = dgn[Sg * cpc + idx];
+        dp[C] = idx < kThreads ? st0[0] : idx < 2 * kThreads ? st1[0] : e[0];
+        dp[2 * C] = idx < kThreads ? st0[1] : idx < 2 * kThreads ? st1[1] : e[1];
         dp[3 * C] = red[(Sg + s) * ldred + cl];
       }
     }
@@ -798,6 +806,14 @@ __global__ void __launch_bounds__(kThreads, 1) lstmp_bwd_tma_kernel(const __grid
   // bias / peephole gradients of my cells: sum over the streams in a fixed order; per-group partials when the streams
   // are split into groups (summed by small_grads_kernel), else straight into the gradient arena
   // (bias(4C) | peephole_i | peephole_f | peephole_o are contiguous there, LPS.h:162-189)
+  __syncthreads();
+  float* acc7 = reinterpret_cast<float*>(rg.ring);  // [Sg*nc][7]: the operand ring is idle now
+  for (int idx = tid; idx < Sg * nc; idx += kThreads) {
+    const float* e = ext + (size_t)(idx - 2 * kThreads) * 10;
+#pragma unroll
+    for (int w = 0; w < 7; ++w)
+      acc7[(size_t)idx * 7 + w] = idx < kThreads ? st0[3 + w] : idx < 2 * kThreads ? st1[3 + w] : e[3 + w];
+  }
   __syncthreads();
   float* gsm = p.g_small + (size_t)grp * 7 * C;
   for (int q = tid; q < nc * 7; q += kThreads) {
@@ -946,8 +962,10 @@ bool bwd_tma_plan(int C, int R, int S, int G, int nctas, int kp, size_t smem_lim
   p->off_ring = (unsigned)off;
   const int ldred = ((rpb > cpc ? rpb : cpc) | 1);
   p->ldred = (unsigned)ldred;
-  const size_t tail = round1k((size_t)128 * ldred * 4) + round1k((size_t)2 * Sg * cpc * 4) +
-                      round1k((size_t)Sg * cpc * 4) + round1k((size_t)Sg * cpc * 7 * 4) + 1024 + 1024;
+  const int red_rows = (2 * Sg + 31) & ~31;
+  const size_t n_ext = Sg * cpc > 2 * kThreads ? (size_t)(Sg * cpc - 2 * kThreads) : 0;
+  // (the bias / peephole sums are reduced through the idle ring at the end of the kernel: [Sg*cpc][7] floats)
+  const size_t tail = round1k((size_t)red_rows * ldred * 4) + round1k(n_ext * 10 * 4) + 1024 + 1024;
   const size_t reserve = 1024 + (size_t)static_smem_reserve();
   if (smem_limit < off + tail + reserve) return false;
   int nslot = 0, gt = 1;
@@ -958,10 +976,9 @@ bool bwd_tma_plan(int C, int R, int S, int G, int nctas, int kp, size_t smem_lim
   p->gt = gt;
   p->slot_bytes = slot_bytes;
   off += (size_t)nslot * slot_bytes;
-  p->off_red = take((size_t)128 * ldred * 4);
-  p->off_dgn = take((size_t)2 * Sg * cpc * 4);
-  p->off_dcn = take((size_t)Sg * cpc * 4);
-  p->off_acc7 = take((size_t)Sg * cpc * 7 * 4);
+  if ((size_t)nslot * slot_bytes < (size_t)Sg * cpc * 7 * 4) return false;
+  p->off_red = take((size_t)red_rows * ldred * 4);
+  p->off_ext = take(n_ext * 10 * 4);
   p->off_peep = take((size_t)3 * cpc * 4);
   p->off_bars = take(256);
   *smem_bytes = off + 1024;
