@@ -116,3 +116,17 @@ def test_copy_is_deep(fake):
     assert twin.engine.get_state()[0].sum() == 8.0 and twin.GetTrainOptions().momentum == 0.9
     twin.SetParams(np.zeros(twin.NumParams(), np.float32))
     assert np.abs(c.GetParams()).max() > 0
+
+
+def test_time_shift_mirror_config_parsing():
+    """TimeShift::InitData (standard/nnet/nnet-time-shift.h:21-30): <Shift> n, anything else is a KALDI_ERR."""
+    import pytest
+    import kaldi_lstm_b200 as klb
+    ts = klb.TimeShift(40)
+    ts.InitData("<Shift> 5")
+    assert ts.shift_ == 5 and ts.GetType() == "TimeShift" and ts.input_dim_ == ts.output_dim_ == 40
+    ts.InitData("<Shift> -3")
+    assert ts.shift_ == -3
+    with pytest.raises(RuntimeError):
+        ts.InitData("<Shfit> 3")
+    assert ts.BackpropagateFnc(None, None, None, None) is None   # meaningless in the reference too (:53-56)

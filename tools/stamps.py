@@ -5,7 +5,7 @@ os.environ["LSTMP_B200_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.p
 import torch
 import kaldi_lstm_b200 as klb
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-T = 4
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 comp = klb.LstmProjectedStreams(40, 512, max_frames=T)
 comp.InitData("<CellDim> 800 <NumStream> %d <ParamScale> 0.01" % S)
 x = torch.randn(T * S, 40, device="cuda")
