@@ -42,3 +42,15 @@ def test_cpp_xent_mirror_on_gpu():
     print(r.stdout, r.stderr)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
 
+
+
+@pytest.mark.gpu
+def test_cpp_trainer_loop_on_gpu():
+    """tests/cpp/trainer_test.cc: the reference trainer's main loop (bd-nnet-train-lstm-streams.cc:143-229) in C++ over
+    B200StreamDispatch + B200LstmProjectedStreams + B200AffineSoftmaxXent -- frame accounting, cross-validation mode,
+    decreasing loss."""
+    _build()
+    tbin = os.path.join(ROOT, "tests", "cpp", "_build", "trainer_test")
+    r = subprocess.run([tbin], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
