@@ -246,8 +246,7 @@ __device__ __forceinline__ void tma_product(Pipe& ps, const Ring& rg, GridSync& 
     float* rr = red + (size_t)row * ldred;
     for (int c = 0; c < nvalid; c += 16) {
       float a[16], b[16];
-      tc::tmem_ld16(taddr + (uint32_t)c, a);
-      tc::tmem_ld16(taddr + (uint32_t)(nh + c), b);
+      tc::tmem_ld16x2(taddr + (uint32_t)c, taddr + (uint32_t)(nh + c), a, b);
 #pragma unroll
       for (int q = 0; q < 16; ++q)
         if (c + q < nvalid) rr[c + q] = a[q] + b[q];
