@@ -14,6 +14,14 @@
  *   lstmp_b200_backpropagate       BackpropagateFnc(in, out, out_diff, in_diff) LPS.h:334-499
  *   lstmp_b200_update              momentum accumulation + Update()            LPS.h:465-487,501-512
  *
+ * and, one row of SURVEY.md section 8(f) at a time, the callers and data formats either side of that layer:
+ *
+ *   lstmp_b200_xent_*              Xent::EvalMasked + Report (sparse targets)  google/nnet/nnet-loss.cc:76-164,293-307
+ *   lstmp_b200_tail_*              AffineTransform + Softmax + EvalMasked      google/nnet.proto:4-5, TRAIN.cc:215-228
+ *   lstmp_b200_dispatch_*          multi-stream chunk assembly + CMVN           TRAIN.cc:146-212, feature_transform.nnet.txt
+ *   lstmp_b200_time_shift, lstmp_b200_update_clipped     the standard/ version's TimeShift and gradient clip
+ *   lstmp_b200_allreduce_grads_nccl, lstmp_b200_set_nccl stream-sharded data parallelism (new relative to the reference)
+ *
  * The kernels fused behind these calls also replace google/cudamatrix/bd-cu-kernels.cu
  * (cudaF_add_mat_diag_vec / cudaF_add_mat_dot_mat, bd-cu-kernels-ansi.h:9-22) and the
  * CuMatrixBase methods listed in SURVEY.md section 8a (a6-a10).

@@ -1,24 +1,28 @@
-// TMA-fed tcgen05 time loops for LstmProjectedStreams on sm_100a: forward (LPS.h:261-331) and the mirrored
-// truncated-BPTT backward (LPS.h:369-454), one persistent launch per chunk and direction, num_stream <= 64.
-// (LPS.h = google/nnet/bd-nnet-lstm-projected-streams.h of the reference.)
+// tcgen05 time loops for LstmProjectedStreams on sm_100a, fed by bulk copies (the TMA unit's cp.async.bulk): forward
+// (LPS.h:261-331) and the mirrored truncated-BPTT backward (LPS.h:369-454), one persistent launch per chunk and
+// direction, <= 64 streams per stream group.  (LPS.h = google/nnet/bd-nnet-lstm-projected-streams.h of the reference.)
 //
 // Every per-timestep contraction is  D[128 x N] (TMEM, fp32) += A[128 x 16] * B[N x 16]^T  (tcgen05.mma.kind::f16,
 // bf16 operands).  FP32 fidelity comes from a two-piece bf16 split  x = hi + lo  (hi = bf16(x), lo = bf16(x - hi))
 // of BOTH operands, stacked instead of issued as extra instructions:
-//   A rows 0..S-1   = hi halves of the all-gathered activations of all streams, rows 64..64+S-1 = lo halves;
-//   B rows 0..n-1   = hi halves of the CTA's stationary weight slice,           rows n..2n-1    = lo halves;
-// one MMA yields all four cross products, result[s][j] = D[s][j] + D[s][n+j] + D[64+s][j] + D[64+s][n+j]
+//   A rows 0..Sg-1  = hi halves of the all-gathered activations of the group's streams, rows Sg..2Sg-1 = lo halves;
+//   B rows 0..n-1   = hi halves of the CTA's stationary weight slice,                   rows n..2n-1   = lo halves;
+// one MMA yields all four cross products, result[s][j] = D[s][j] + D[s][n+j] + D[Sg+s][j] + D[Sg+s][n+j]
 // (relative error ~4e-6 end to end, tools/split_precision_study.py; the path's tolerance is 1e-4).
 //
 // The PRODUCER of an activation splits it: the CTA that computes r(t) / m(t) / d_r(t) / DGIFO(t) writes the hi and lo
-// bf16 halves to small global arrays ([2][S][K], L2-resident), and after the grid barrier every consumer pulls
-// [S rows x 64 k] boxes of both straight into a SWIZZLE_128B shared-memory ring with cp.async.bulk.tensor (TMA,
-// mbarrier expect_tx).  The operands reach shared memory through the async proxy: no loader warps, no register pass,
-// no generic stores, no proxy-fence relay -- one elected thread issues the copies, one issues the MMAs.
+// bf16 halves straight into small global "tile image" arrays -- per stream group and 64-k chunk the ready-made
+// SWIZZLE_128B K-major shared-memory image [hi rows | lo rows] x 128 bytes (store_hl), L2-resident -- and after the grid
+// barrier every consumer pulls groups of consecutive tile images into a shared-memory ring with ONE cp.async.bulk each
+// (SASS UBLKCP, mbarrier expect_tx).  The operands reach shared memory through the async proxy: no loader warps, no
+// register pass, no generic stores into operand tiles, no proxy-fence relay -- up to three threads issue the copies,
+// one warp issues the MMAs.  (Tensor-map copies, cp.async.bulk.tensor, were measured first: one 128-byte row per ~3.5
+// cycles, 36-43 B/clk per SM -- DESIGN.md section 3.1.)  The grid barrier is split and run by ONE thread (GridSync):
+// only the copies depend on other CTAs' data; the activation record goes to HBM after the arrive.
 //
 // Backward decomposition (the reason it differs from forward): d_r(t) = out_diff(t) + DGIFO(t+1) * W_gifo_r contracts
 // over K = 4C.  CTAs form clusters of kp; cluster b owns ~R/np columns of d_r, CTA rank a of the cluster contracts the
-// a-th K slice (TMA gather of 4C/kp columns of DGIFO(t+1) only) and the kp partial [S x R/np] blocks are summed through
+// a-th K slice (it gathers 4C/kp columns of DGIFO(t+1) only) and the kp partial [Sg x R/np] blocks are summed through
 // distributed shared memory (a cluster barrier, not a grid barrier).  d_m(t) = d_r(t) * W_r_m and the derivative
 // chain run cell-sliced over all CTAs as in forward.  Two grid barriers per timestep in both directions.
 #include <cuda_bf16.h>
