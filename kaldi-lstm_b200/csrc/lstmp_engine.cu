@@ -87,6 +87,7 @@ struct lstmp_b200_engine {
   bool have_bwd = false; // a backpropagate record exists for T_last
   unsigned long long launches = 0;
   int gemm_backend = 0;
+  bool dual_wgrad = true;  // G(w_gifo_x) and G(w_gifo_r) in one launch (LSTMP_B200_DUAL_WGRAD=0: two launches)
   HlWorkspace hlws;
   // data-parallel exchange overlapped with the backward pass (lstmp_b200_set_nccl)
   void* nccl_comm = nullptr;
@@ -376,6 +377,7 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
   // 2 (default): bf16 hi/lo tile images + bulk copies (lstmp_gemm_hl.cu); 1: 3xTF32 with loader warps; 0: FP32 SIMT
   h->gemm_backend = env_int("LSTMP_B200_GEMM", 2);
   if (h->gemm_backend < 0 || h->gemm_backend > 2) h->gemm_backend = 2;
+  h->dual_wgrad = env_int("LSTMP_B200_DUAL_WGRAD", 1) != 0;
 #endif
   if (h->d.dbg & 12) {
     if (cudaMalloc((void**)&h->dbg_stamps, (2 + 2 * 1024) * sizeof(long long)) == cudaSuccess)
@@ -806,15 +808,30 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
   if (in_diff && (rc = gemm(h, 3, in_diff, (long long)ld_id, num_rows, I, 4 * C, 1.f, h->dgifo, 4 * C, 0,
                             h->params + h->off_wx, I, 0, 0.f, nullptr, st)))
     return rc;
-  // G(w_gifo_x) = DGIFO[1..T]^T * in                                         (LPS.h:468)
-  if ((rc = gemm(h, 4, h->grads + h->off_wx, I, 4 * C, I, num_rows, 1.f, h->dgifo, 4 * C, 1, in, (long long)ld_in, 0,
-                 0.f, nullptr, st)))
-    return rc;
+  // G(w_gifo_x) = DGIFO[1..T]^T * in  and  G(w_gifo_r) = DGIFO[1..T]^T * R[0..T-1]     (LPS.h:468, 471): both contract
+  // DGIFO^T, so the tile-image back end runs them as ONE persistent launch (DGIFO^T split once, 2 * 7 * 4 output tiles
+  // of the two products share the 148 CTAs instead of two under-filled launches)
+  bool dual_done = false;
+#ifdef LSTMP_HAVE_TC_GEMM
+  if (h->gemm_backend == 2 && h->dual_wgrad) {
+    Timed tm(h, 4, st);
+    int nl = 0;
+    CUDA_TRY(launch_gemm_hl_dual(&h->hlws, 4 * C, num_rows, h->dgifo, 4 * C, 1, h->grads + h->off_wx, I, I, in,
+                                 (long long)ld_in, h->grads + h->off_wr, R, R, h->rbuf, R, st, &dual_done, &nl));
+    h->launches += nl;
+  }
+#endif
+  if (!dual_done) {
+    if ((rc = gemm(h, 4, h->grads + h->off_wx, I, 4 * C, I, num_rows, 1.f, h->dgifo, 4 * C, 1, in, (long long)ld_in, 0,
+                   0.f, nullptr, st)))
+      return rc;
+  }
   if ((rc = exchange_block(h, h->off_wx, (size_t)4 * C * I, st, false))) return rc;
-  // G(w_gifo_r) = DGIFO[1..T]^T * R[0..T-1]                                  (LPS.h:471)
-  if ((rc = gemm(h, 4, h->grads + h->off_wr, R, 4 * C, R, num_rows, 1.f, h->dgifo, 4 * C, 1, h->rbuf, R, 0, 0.f,
-                 nullptr, st, /*reuse_a: DGIFO^T was split for the previous GEMM*/ true)))
-    return rc;
+  if (!dual_done) {
+    if ((rc = gemm(h, 4, h->grads + h->off_wr, R, 4 * C, R, num_rows, 1.f, h->dgifo, 4 * C, 1, h->rbuf, R, 0, 0.f,
+                   nullptr, st, /*reuse_a: DGIFO^T was split for the previous GEMM*/ true)))
+      return rc;
+  }
   // w_gifo_r | bias | peepholes are contiguous in the arena; bias / peepholes were written before the GEMMs
   if ((rc = exchange_block(h, h->off_wr, h->off_wm - h->off_wr, st, false))) return rc;
   // G(w_r_m) = DR[1..T]^T * M[1..T]                                          (LPS.h:486)

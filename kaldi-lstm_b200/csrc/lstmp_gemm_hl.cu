@@ -31,10 +31,11 @@ constexpr int BM = 128, BN = 128, BK = 64;           // tile: 128 x 128 outputs,
 constexpr uint32_t TILE = 128 * 128;                 // bytes of one [128 rows x 64 k] bf16 image (hi or lo)
 constexpr int NSTAGE = 3;                            // stages of A_hi | A_lo | B_hi | B_lo = 64 KB
 constexpr uint32_t STAGE = 4 * TILE;
-constexpr int THREADS = 192;                         // warp 0 producer, warp 1 MMA issuer + TMEM, warps 2-5 epilogue
-constexpr int PLD = 36;                              // row stride (floats) of an epilogue warp's [32 x 32] staging patch
+constexpr int THREADS = 320;                         // warp 0 producer, warp 1 MMA issuer + TMEM, warps 2-9 epilogue
+constexpr int PLD = 20;                              // row stride (floats) of an epilogue warp's [32 x 16] staging patch
 constexpr uint32_t PATCH = 32 * PLD * 4;
-constexpr uint32_t SMEM = NSTAGE * STAGE + 4 * PATCH + 1024 + 256;
+constexpr int NEPI = 8;                              // epilogue warps: two per TMEM lane quadrant (64 columns each)
+constexpr uint32_t SMEM = NSTAGE * STAGE + NEPI * PATCH + 1024 + 256;
 
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
@@ -98,6 +99,64 @@ __global__ void __launch_bounds__(256) split_hl_kernel(uint8_t* __restrict__ img
   }
 }
 
+// Both operands of a GEMM in ONE launch (the direct kernel for each): blocks [0, nblk_a) work on A, the rest on B.
+struct SplitJob {
+  uint8_t* img;
+  const float* src;
+  long long ld;
+  int R, K, nrt, nkt, transposed;
+};
+template <bool TRANSPOSED>
+__device__ __forceinline__ void split_units(const SplitJob& j, long long first, long long stride) {
+  const long long units = (long long)j.nrt * j.nkt * 128 * 8;
+  for (long long u = first; u < units; u += stride) {
+    int rl, kc, kt, rt;
+    if (!TRANSPOSED) {
+      kc = (int)(u & 7);
+      long long t = u >> 3;
+      kt = (int)(t % j.nkt);
+      t /= j.nkt;
+      rl = (int)(t & 127);
+      rt = (int)(t >> 7);
+    } else {
+      rl = (int)(u & 127);
+      long long t = u >> 7;
+      rt = (int)(t % j.nrt);
+      t /= j.nrt;
+      kc = (int)(t & 7);
+      kt = (int)(t >> 3);
+    }
+    const int r = rt * 128 + rl, k0 = kt * BK + kc * 8;
+    float v[8];
+    if (!TRANSPOSED) {
+      if (r < j.R && k0 + 7 < j.K && ((j.ld & 3) == 0)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(j.src + (long long)r * j.ld + k0));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(j.src + (long long)r * j.ld + k0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (r < j.R && k0 + q < j.K) ? __ldg(j.src + (long long)r * j.ld + k0 + q) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = (r < j.R && k0 + q < j.K) ? __ldg(j.src + (long long)(k0 + q) * j.ld + r) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    uint8_t* t = j.img + ((size_t)rt * j.nkt + kt) * 2 * TILE + tc::sw128_off(rl, kc);
+    *reinterpret_cast<uint4*>(t) = hi;
+    *reinterpret_cast<uint4*>(t + TILE) = lo;
+  }
+}
+__global__ void __launch_bounds__(256) split_pair_kernel(const SplitJob ja, const SplitJob jb, int nblk_a) {
+  const bool is_a = (int)blockIdx.x < nblk_a;
+  const SplitJob& j = is_a ? ja : jb;
+  const long long nb = is_a ? nblk_a : (long long)gridDim.x - nblk_a;
+  const long long first = ((long long)(is_a ? blockIdx.x : blockIdx.x - nblk_a)) * blockDim.x + threadIdx.x;
+  if (j.transposed) split_units<true>(j, first, nb * blockDim.x);
+  else split_units<false>(j, first, nb * blockDim.x);
+}
+
 // TRANSPOSED operand (element (r, k) at src[k * ld + r]) through a shared-memory tile: one CTA per [128 r x 64 k] image
 // tile reads 64 source rows of 512 contiguous bytes (coalesced along r) and writes, per image row, the 8 hi units and
 // the 8 lo units = two whole 128-byte lines.  (The direct version above read coalesced but wrote 16-byte pieces to 32
@@ -153,11 +212,14 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t 
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nkt, float alpha_in,
                const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, float beta_in,
-               const float* __restrict__ bias_in, int kt_per_split, int splits, float* __restrict__ split_ws) {
+               const float* __restrict__ bias_in, int kt_per_split, int splits, float* __restrict__ split_ws,
+               float* __restrict__ Cout2, long long ldc_out2, int N2) {
+  // Cout2 != nullptr: TWO products that share op(A) in one launch -- C = A * B1 and C2 = A * B2 -- with the n tiles of
+  // B2's image following those of B1 in b_img (the two weight-gradient GEMMs that both contract DGIFO^T).
   extern __shared__ __align__(128) uint8_t smem_raw_hl[];
   uint8_t* tiles = smem_raw_hl + ((1024u - (smem_u32(smem_raw_hl) & 1023u)) & 1023u);
   float* patches = reinterpret_cast<float*>(tiles + NSTAGE * STAGE);
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * STAGE + 4 * PATCH);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * STAGE + NEPI * PATCH);
   uint64_t* empty = full + NSTAGE;
   uint64_t* acc_full = empty + NSTAGE;   // [2] accumulator buffer complete (MMA warp -> epilogue)
   uint64_t* acc_empty = acc_full + 2;    // [2] accumulator buffer drained (4 epilogue warps -> MMA warp)
@@ -165,7 +227,8 @@ gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nk
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int ntm = (M + BM - 1) / BM, ntn = (N + BN - 1) / BN;
+  const int ntn1 = (N + BN - 1) / BN;
+  const int ntm = (M + BM - 1) / BM, ntn = ntn1 + (Cout2 ? (N2 + BN - 1) / BN : 0);
   const int nitems = ntm * ntn * splits;
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -174,7 +237,7 @@ gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nk
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);
+      mbar_init(&acc_empty[b], NEPI);
     }
     fence_mbar_init();
   }
@@ -248,16 +311,19 @@ gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nk
     }
     tc::tc_fence_before();
   } else {
-    // ------------------------------ epilogue (warps 2-5: TMEM lane quadrants 2, 3, 0, 1) -----
+    // ------------------------------ epilogue (warps 2-9: TMEM lane quadrants 2, 3, 0, 1, 2, 3, 0, 1) -----
     const int quad = warp & 3;
+    const int N_first = N;
     uint32_t it = 0;
     for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
       const int mt = w % ntm, nt = (w / ntm) % ntn, z = w / (ntm * ntn);
-      const int m0 = mt * BM, n0 = nt * BN;
-      float* Cm = Cout;
-      long long ldc = ldc_out;
+      const bool second = nt >= ntn1;            // (dual launch) this n tile belongs to the second product
+      const int m0 = mt * BM, n0 = (second ? nt - ntn1 : nt) * BN;
+      const int N = second ? N2 : N_first;
+      float* Cm = second ? Cout2 : Cout;
+      long long ldc = second ? ldc_out2 : ldc_out;
       float alpha = alpha_in, beta = beta_in;
-      const float* bias = bias_in;
+      const float* bias = second ? nullptr : bias_in;
       if (split_ws) {  // split-K: raw partial sums to split_ws[z][M x N]; splitk_reduce applies alpha / beta / bias
         Cm = split_ws + (size_t)z * M * N;
         ldc = N;
@@ -270,28 +336,25 @@ gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nk
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16);
       float* patch = patches + (size_t)(warp - 2) * (PATCH / 4);
-      // 32 columns at a time: TMEM lane (= row) -> this warp's staging patch -> global memory with 8 lanes per row,
-      // i.e. whole 128-byte lines per store instruction (4 rows each) instead of 32 scattered 16-byte pieces
-      const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+      // 16 columns at a time: TMEM lane (= row) -> this warp's staging patch -> global memory with 4 lanes per row
+      // (64 contiguous bytes), 8 rows per store instruction.  Two warps share a lane quadrant (column halves).
+      const int half = (warp - 2) >> 2;
+      const int rsub = lane >> 2, c4 = (lane & 3) * 4;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[16], v2[16];
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
+        float v[16];
         tc::tmem_ld16(taddr + (uint32_t)c, v);
-        tc::tmem_ld16(taddr + (uint32_t)(c + 16), v2);
         float* prow = patch + lane * PLD;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          *reinterpret_cast<float4*>(prow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          *reinterpret_cast<float4*>(prow + 16 + j) = make_float4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
-        }
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(prow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
         const int gn = n0 + c + c4;
         const bool vec_ok = ((ldc & 3) == 0) && gn + 3 < N;
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias && vec_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + gn));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = rsub + 4 * i;
+        for (int i = 0; i < 4; ++i) {
+          const int rl = rsub + 8 * i;
           const int gm = m0 + quad * 32 + rl;
           if (gm < M) {
             const float4 a4 = *reinterpret_cast<const float4*>(patch + rl * PLD + c4);
@@ -358,7 +421,7 @@ cudaError_t gemm_hl_split(uint8_t* img, const float* src, long long ld, int rows
 
 cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alpha, const uint8_t* a_img,
                         const uint8_t* b_img, float beta, const float* bias, cudaStream_t stream, float* ws,
-                        size_t ws_floats, int* nlaunch) {
+                        size_t ws_floats, int* nlaunch, float* C2 = nullptr, long long ldc2 = 0, int N2 = 0) {
   *nlaunch = 1;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -370,13 +433,14 @@ cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alph
     attr_set[dev & 63] = true;
   }
   const int nkt = (K + hl::BK - 1) / hl::BK;
-  const int ntm = (M + hl::BM - 1) / hl::BM, ntn = (N + hl::BN - 1) / hl::BN;
+  const int ntm = (M + hl::BM - 1) / hl::BM,
+            ntn = (N + hl::BN - 1) / hl::BN + (C2 ? (N2 + hl::BN - 1) / hl::BN : 0);
   const int tiles = ntm * ntn;
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   int splits = 1;
-  // split-K when the output tiles alone cannot fill the SMs (in_diff: 40 tiles, G(w_r_m): 28 tiles)
-  if (ws && tiles < 100 && nkt >= 4 && (N & 3) == 0) {
+  // split-K when the output tiles alone cannot fill the SMs (in_diff: 40 tiles, G(w_r_m): 28 tiles); never for a dual launch
+  if (!C2 && ws && tiles < 100 && nkt >= 4 && (N & 3) == 0) {
     splits = nsm / tiles;
     if (splits > 8) splits = 8;
     if (splits > nkt / 2) splits = nkt / 2;
@@ -390,7 +454,7 @@ cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alph
   const int items = tiles * splits;
   dim3 grid(items < nsm ? items : nsm), block(hl::THREADS);
   hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(C, ldc, M, N, nkt, alpha, a_img, b_img, beta, bias, kts, splits,
-                                                        splits > 1 ? ws : nullptr);
+                                                        splits > 1 ? ws : nullptr, C2, ldc2, N2);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (splits > 1) {
@@ -398,6 +462,21 @@ cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alph
     return launch_splitk_reduce(C, ldc, M, N, alpha, beta, bias, ws, splits, stream);
   }
   return cudaSuccess;
+}
+
+static hl::SplitJob make_job(uint8_t* img, const float* src, long long ld, int rows, int K, bool transposed, int* blocks,
+                             bool* tiled) {
+  hl::SplitJob j;
+  j.img = img; j.src = src; j.ld = ld; j.R = rows; j.K = K;
+  j.nrt = (rows + 127) / 128;
+  j.nkt = (K + hl::BK - 1) / hl::BK;
+  j.transposed = transposed ? 1 : 0;
+  const long long units = (long long)j.nrt * j.nkt * 128 * 8;
+  int b = (int)((units + 255) / 256);
+  if (b > 148 * 8) b = 148 * 8;
+  *blocks = b;
+  *tiled = transposed && j.nrt * j.nkt >= 2 * 148;
+  return j;
 }
 
 // One call = split both operands (unless the caller says op(A)'s image of the previous call is still valid), run the
@@ -423,22 +502,77 @@ cudaError_t launch_gemm_hl(HlWorkspace* w, float* C, long long ldc, int M, int N
     if (e == cudaSuccess) *cap = need;
     return e;
   };
-  if (!(reuse_a && w->a && w->a_bytes == na)) {
-    cudaError_t e = grow(&w->a, &w->a_cap, na);
-    if (e != cudaSuccess) return e;
-    e = gemm_hl_split(w->a, A, lda, M, K, tA != 0, stream);
-    if (e != cudaSuccess) return e;
+  const bool need_a = !(reuse_a && w->a && w->a_bytes == na);
+  cudaError_t e = cudaSuccess;
+  if (need_a && (e = grow(&w->a, &w->a_cap, na)) != cudaSuccess) return e;
+  if ((e = grow(&w->b, &w->b_cap, nb)) != cudaSuccess) return e;
+  int ba = 0, bb = 0;
+  bool ta = false, tb = false;
+  const hl::SplitJob ja = make_job(w->a, A, lda, M, K, tA != 0, &ba, &ta);
+  const hl::SplitJob jb = make_job(w->b, B, ldb, N, K, tB == 0, &bb, &tb);
+  if (need_a && !ta && !tb) {
+    // both operands in one launch
+    hl::split_pair_kernel<<<ba + bb, 256, 0, stream>>>(ja, jb, ba);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     w->a_bytes = na;
     ++*nlaunch;
+  } else {
+    if (need_a) {
+      if ((e = gemm_hl_split(w->a, A, lda, M, K, tA != 0, stream)) != cudaSuccess) return e;
+      w->a_bytes = na;
+      ++*nlaunch;
+    }
+    if ((e = gemm_hl_split(w->b, B, ldb, N, K, tB == 0, stream)) != cudaSuccess) return e;
+    ++*nlaunch;
   }
-  cudaError_t e = grow(&w->b, &w->b_cap, nb);
-  if (e != cudaSuccess) return e;
-  e = gemm_hl_split(w->b, B, ldb, N, K, tB == 0, stream);
-  if (e != cudaSuccess) return e;
-  ++*nlaunch;
   int nl = 0;
   e = gemm_hl_run(C, ldc, M, N, K, alpha, w->a, w->b, beta, bias, stream, ws, ws_floats, &nl);
   *nlaunch += nl;
+  *handled = true;
+  return e;
+}
+
+// C1[M x N1] = op(A) * B1 and C2[M x N2] = op(A) * B2 in ONE launch (alpha = 1, beta = 0, no bias): op(A) is split
+// once, B1 and B2 (both stored [K x N], n contiguous) are split into consecutive n tiles of one image.  The two
+// weight-gradient GEMMs of a layer that contract DGIFO^T: G(w_gifo_x) = DGIFO^T * in, G(w_gifo_r) = DGIFO^T * R.
+cudaError_t launch_gemm_hl_dual(HlWorkspace* w, int M, int K, const float* A, long long lda, int tA, float* C1,
+                                long long ldc1, int N1, const float* B1, long long ldb1, float* C2, long long ldc2, int N2,
+                                const float* B2, long long ldb2, cudaStream_t stream, bool* handled, int* nlaunch) {
+  *handled = false;
+  *nlaunch = 0;
+  if (!w || M <= 0 || N1 <= 0 || N2 <= 0 || K <= 0) return cudaSuccess;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(C1) || !al16(C2) || !al16(A) || !al16(B1) || !al16(B2)) return cudaSuccess;
+  const size_t na = gemm_hl_image_bytes(M, K), nb1 = gemm_hl_image_bytes(N1, K), nb2 = gemm_hl_image_bytes(N2, K);
+  auto grow = [&](uint8_t** p, size_t* cap, size_t need) -> cudaError_t {
+    if (need <= *cap) return cudaSuccess;
+    if (*p) {
+      cudaError_t e = cudaFree(*p);
+      if (e != cudaSuccess) return e;
+      *p = nullptr;
+      *cap = 0;
+    }
+    cudaError_t e = cudaMalloc((void**)p, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+  };
+  cudaError_t e;
+  int b1 = 0, b2 = 0;
+  bool t1 = false, t2 = false;
+  make_job(nullptr, B1, ldb1, N1, K, true, &b1, &t1);
+  make_job(nullptr, B2, ldb2, N2, K, true, &b2, &t2);
+  if (t1 || t2) return cudaSuccess;  // operands large enough for the tiled transposed split: two ordinary GEMMs
+  if ((e = grow(&w->a, &w->a_cap, na)) != cudaSuccess) return e;
+  if ((e = grow(&w->b, &w->b_cap, nb1 + nb2)) != cudaSuccess) return e;
+  if ((e = gemm_hl_split(w->a, A, lda, M, K, tA != 0, stream)) != cudaSuccess) return e;
+  w->a_bytes = na;
+  const hl::SplitJob j1 = make_job(w->b, B1, ldb1, N1, K, true, &b1, &t1);
+  const hl::SplitJob j2 = make_job(w->b + nb1, B2, ldb2, N2, K, true, &b2, &t2);
+  hl::split_pair_kernel<<<b1 + b2, 256, 0, stream>>>(j1, j2, b1);   // (direct kernel for both: these operands are small)
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  int nl = 0;
+  e = gemm_hl_run(C1, ldc1, M, N1, K, 1.f, w->a, w->b, 0.f, nullptr, stream, nullptr, 0, &nl, C2, ldc2, N2);
+  *nlaunch = 2 + nl;
   *handled = true;
   return e;
 }

@@ -139,6 +139,9 @@ struct HlWorkspace {
 cudaError_t launch_gemm_hl(HlWorkspace* w, float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
                            long long lda, int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
                            cudaStream_t stream, bool* handled, float* ws, size_t ws_floats, int* nlaunch, bool reuse_a);
+cudaError_t launch_gemm_hl_dual(HlWorkspace* w, int M, int K, const float* A, long long lda, int tA, float* C1,
+                                long long ldc1, int N1, const float* B1, long long ldb1, float* C2, long long ldc2, int N2,
+                                const float* B2, long long ldb2, cudaStream_t stream, bool* handled, int* nlaunch);
 void gemm_hl_free(HlWorkspace* w);
 
 // corr = G + momentum*corr ; param -= lr*corr   over the flat arena
