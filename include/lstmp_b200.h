@@ -181,6 +181,26 @@ int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, int N, int K
                           size_t lda, int tA, const float* B, size_t ldb, int tB, float beta, const float* bias,
                           void* stream);
 
+/* Test hook for the grouped launch the engine uses after a layer's backward time loop (in_diff, G(w_gifo_x),
+ * G(w_gifo_r), G(w_r_m): LPS.h:457, 468, 471, 486 -- four AddMatMat calls in the reference): up to 4 independent
+ * products, same argument meaning as lstmp_b200_debug_gemm, run as one operand-split launch + one persistent tcgen05
+ * launch + one split-K reduce.  Returns the number of kernel launches (>= 2) or a negative LSTMP_B200_E* code. */
+typedef struct lstmp_b200_gemm_desc {
+  float* C;
+  size_t ldc;
+  int M, N, K;
+  float alpha;
+  const float* A;
+  size_t lda;
+  int tA;
+  const float* B;
+  size_t ldb;
+  int tB;
+  float beta;
+  const float* bias;
+} lstmp_b200_gemm_desc;
+int lstmp_b200_debug_gemm_group(int n, const lstmp_b200_gemm_desc* d, void* stream);
+
 /* Update with the element-wise gradient clipping of the single-stream `standard/` component
  * (standard/nnet/nnet-lstm-projected.h:469-493): corr = G + momentum*corr (the AddMatMat beta of :438-460); every
  * element of corr clamped to [-max_grad, +max_grad] IN PLACE (ClipGradMat / ClipGradVec, :469-478, max_grad = 50 at

@@ -87,7 +87,7 @@ struct lstmp_b200_engine {
   bool have_bwd = false; // a backpropagate record exists for T_last
   unsigned long long launches = 0;
   int gemm_backend = 0;
-  bool dual_wgrad = true;  // G(w_gifo_x) and G(w_gifo_r) in one launch (LSTMP_B200_DUAL_WGRAD=0: two launches)
+  bool group_bwd_gemms = true;  // the GEMMs after the backward loop as one group (LSTMP_B200_GROUP_GEMMS=0: one by one)
   HlWorkspace hlws;
   // data-parallel exchange overlapped with the backward pass (lstmp_b200_set_nccl)
   void* nccl_comm = nullptr;
@@ -377,7 +377,7 @@ extern "C" int lstmp_b200_create(int I, int C, int R, int S, int Tmax, int devic
   // 2 (default): bf16 hi/lo tile images + bulk copies (lstmp_gemm_hl.cu); 1: 3xTF32 with loader warps; 0: FP32 SIMT
   h->gemm_backend = env_int("LSTMP_B200_GEMM", 2);
   if (h->gemm_backend < 0 || h->gemm_backend > 2) h->gemm_backend = 2;
-  h->dual_wgrad = env_int("LSTMP_B200_DUAL_WGRAD", 1) != 0;
+  h->group_bwd_gemms = env_int("LSTMP_B200_GROUP_GEMMS", 1) != 0;
 #endif
   if (h->d.dbg & 12) {
     if (cudaMalloc((void**)&h->dbg_stamps, (2 + 2 * 1024) * sizeof(long long)) == cudaSuccess)
@@ -804,39 +804,51 @@ extern "C" int lstmp_b200_backpropagate(lstmp_b200_handle_t h, const float* in, 
   }
   h->launches++;
   }
-  // in_diff = DGIFO[1..T] * w_gifo_x                                        (LPS.h:457)
-  if (in_diff && (rc = gemm(h, 3, in_diff, (long long)ld_id, num_rows, I, 4 * C, 1.f, h->dgifo, 4 * C, 0,
-                            h->params + h->off_wx, I, 0, 0.f, nullptr, st)))
-    return rc;
-  // G(w_gifo_x) = DGIFO[1..T]^T * in  and  G(w_gifo_r) = DGIFO[1..T]^T * R[0..T-1]     (LPS.h:468, 471): both contract
-  // DGIFO^T, so the tile-image back end runs them as ONE persistent launch (DGIFO^T split once, 2 * 7 * 4 output tiles
-  // of the two products share the 148 CTAs instead of two under-filled launches)
-  bool dual_done = false;
+  // The four contractions that follow the time loop are independent of each other:
+  //   in_diff     = DGIFO[1..T]   * w_gifo_x        (LPS.h:457)
+  //   G(w_gifo_x) = DGIFO[1..T]^T * in              (LPS.h:468)
+  //   G(w_gifo_r) = DGIFO[1..T]^T * R[0..T-1]       (LPS.h:471)
+  //   G(w_r_m)    = DR[1..T]^T    * M[1..T]         (LPS.h:486)
+  // The tile-image back end runs them as ONE group: every operand split in one launch (DGIFO^T once for both of its
+  // products), every product in one persistent launch whose work items share the 148 CTAs, one split-K reduce.
+  bool grouped = false;
 #ifdef LSTMP_HAVE_TC_GEMM
-  if (h->gemm_backend == 2 && h->dual_wgrad) {
+  if (h->gemm_backend == 2 && h->group_bwd_gemms) {
     Timed tm(h, 4, st);
+    HlGemmDesc d[4];
+    int n = 0;
+    if (in_diff)
+      d[n++] = HlGemmDesc{in_diff, (long long)ld_id, num_rows, I, 4 * C, 1.f, h->dgifo, 4 * C, 0,
+                          h->params + h->off_wx, I, 0, 0.f, nullptr};
+    d[n++] = HlGemmDesc{h->grads + h->off_wx, I, 4 * C, I, num_rows, 1.f, h->dgifo, 4 * C, 1, in, (long long)ld_in, 0, 0.f,
+                        nullptr};
+    d[n++] = HlGemmDesc{h->grads + h->off_wr, R, 4 * C, R, num_rows, 1.f, h->dgifo, 4 * C, 1, h->rbuf, R, 0, 0.f, nullptr};
+    d[n++] = HlGemmDesc{h->grads + h->off_wm, C, R, C, num_rows, 1.f, h->dr, R, 1, h->mbuf, C, 0, 0.f, nullptr};
     int nl = 0;
-    CUDA_TRY(launch_gemm_hl_dual(&h->hlws, 4 * C, num_rows, h->dgifo, 4 * C, 1, h->grads + h->off_wx, I, I, in,
-                                 (long long)ld_in, h->grads + h->off_wr, R, R, h->rbuf, R, st, &dual_done, &nl));
+    CUDA_TRY(launch_gemm_hl_group(&h->hlws, d, n, st, &grouped, h->gemm_ws, h->gemm_ws_floats, &nl));
     h->launches += nl;
   }
 #endif
-  if (!dual_done) {
+  if (!grouped) {
+    if (in_diff && (rc = gemm(h, 3, in_diff, (long long)ld_id, num_rows, I, 4 * C, 1.f, h->dgifo, 4 * C, 0,
+                              h->params + h->off_wx, I, 0, 0.f, nullptr, st)))
+      return rc;
     if ((rc = gemm(h, 4, h->grads + h->off_wx, I, 4 * C, I, num_rows, 1.f, h->dgifo, 4 * C, 1, in, (long long)ld_in, 0,
                    0.f, nullptr, st)))
       return rc;
   }
   if ((rc = exchange_block(h, h->off_wx, (size_t)4 * C * I, st, false))) return rc;
-  if (!dual_done) {
+  if (!grouped) {
     if ((rc = gemm(h, 4, h->grads + h->off_wr, R, 4 * C, R, num_rows, 1.f, h->dgifo, 4 * C, 1, h->rbuf, R, 0, 0.f,
                    nullptr, st, /*reuse_a: DGIFO^T was split for the previous GEMM*/ true)))
       return rc;
   }
   // w_gifo_r | bias | peepholes are contiguous in the arena; bias / peepholes were written before the GEMMs
   if ((rc = exchange_block(h, h->off_wr, h->off_wm - h->off_wr, st, false))) return rc;
-  // G(w_r_m) = DR[1..T]^T * M[1..T]                                          (LPS.h:486)
-  if ((rc = gemm(h, 4, h->grads + h->off_wm, C, R, C, num_rows, 1.f, h->dr, R, 1, h->mbuf, C, 0, 0.f, nullptr, st)))
-    return rc;
+  if (!grouped) {
+    if ((rc = gemm(h, 4, h->grads + h->off_wm, C, R, C, num_rows, 1.f, h->dr, R, 1, h->mbuf, C, 0, 0.f, nullptr, st)))
+      return rc;
+  }
   if ((rc = exchange_block(h, h->off_wm, (size_t)R * C, st, true))) return rc;
   h->have_bwd = true;
   return 0;
@@ -1011,4 +1023,26 @@ extern "C" int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, i
   }
 #endif
   return fail(LSTMP_B200_EUNSUPPORTED, "unknown GEMM backend %d", backend);
+}
+
+extern "C" int lstmp_b200_debug_gemm_group(int n, const lstmp_b200_gemm_desc* d, void* stream) {
+#ifdef LSTMP_HAVE_TC_GEMM
+  if (!d || n < 1 || n > 4) return fail(LSTMP_B200_EINVAL, "gemm group: 1..4 products");
+  HlGemmDesc g[4];
+  for (int i = 0; i < n; ++i)
+    g[i] = HlGemmDesc{d[i].C, (long long)d[i].ldc, d[i].M, d[i].N, d[i].K, d[i].alpha, d[i].A, (long long)d[i].lda, d[i].tA,
+                      d[i].B, (long long)d[i].ldb, d[i].tB, d[i].beta, d[i].bias};
+  bool handled = false;
+  int nl = 0;
+  static HlWorkspace dbg_hl;          // test hook only
+  static float* dbg_ws = nullptr;
+  const size_t dbg_ws_floats = (size_t)4 << 20;
+  if (!dbg_ws && cudaMalloc((void**)&dbg_ws, dbg_ws_floats * sizeof(float)) != cudaSuccess) dbg_ws = nullptr;
+  CUDA_TRY(launch_gemm_hl_group(&dbg_hl, g, n, (cudaStream_t)stream, &handled, dbg_ws, dbg_ws ? dbg_ws_floats : 0, &nl));
+  if (!handled) return fail(LSTMP_B200_EUNSUPPORTED, "bf16 hi/lo GEMM group does not handle this alignment");
+  return nl;
+#else
+  (void)n; (void)d; (void)stream;
+  return fail(LSTMP_B200_EUNSUPPORTED, "built without the tensor-core GEMMs");
+#endif
 }

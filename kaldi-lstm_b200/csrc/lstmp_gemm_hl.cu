@@ -20,6 +20,10 @@
 // with eight loader warps and reaches ~1.9 k cycles per block against 0.78 k of MMA time)
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "lstmp_common.cuh"
 #include "lstmp_kernels.h"
@@ -161,11 +165,10 @@ __global__ void __launch_bounds__(256) split_pair_kernel(const SplitJob ja, cons
 // tile reads 64 source rows of 512 contiguous bytes (coalesced along r) and writes, per image row, the 8 hi units and
 // the 8 lo units = two whole 128-byte lines.  (The direct version above read coalesced but wrote 16-byte pieces to 32
 // different lines per warp: 11.4 us for DGIFO^T [3200 x 1280] against 6.5 us of HBM time.)
-__global__ void __launch_bounds__(256) split_hl_transposed_tiled_kernel(uint8_t* __restrict__ img,
-                                                                        const float* __restrict__ src, long long ld,
-                                                                        int R, int K, int nrt, int nkt) {
-  __shared__ float tile[BK][129];
-  const int rt = blockIdx.x % nrt, kt = blockIdx.x / nrt;
+__device__ __forceinline__ void split_tile_transposed(uint8_t* __restrict__ img, const float* __restrict__ src,
+                                                      long long ld, int R, int K, int nrt, int nkt, int tile_id,
+                                                      float (*tile)[129]) {
+  const int rt = tile_id % nrt, kt = tile_id / nrt;
   const int r0 = rt * 128, k0 = kt * BK;
   const int tid = threadIdx.x;
   for (int i = tid; i < BK * 128; i += 256) {
@@ -187,6 +190,83 @@ __global__ void __launch_bounds__(256) split_hl_transposed_tiled_kernel(uint8_t*
     *reinterpret_cast<uint4*>(t + TILE + off) = lo;
   }
 }
+__global__ void __launch_bounds__(256) split_hl_transposed_tiled_kernel(uint8_t* __restrict__ img,
+                                                                        const float* __restrict__ src, long long ld,
+                                                                        int R, int K, int nrt, int nkt) {
+  __shared__ float tile[BK][129];
+  split_tile_transposed(img, src, ld, R, K, nrt, nkt, blockIdx.x, tile);
+}
+
+// Every operand of a GROUP of GEMMs in ONE launch: blocks [blk0[i], blk0[i + 1]) work on job i; SplitJob::transposed
+// = 0 direct, 1 direct transposed, 2 transposed through the shared-memory tile (one [128 x 64] image tile at a time).
+constexpr int MAX_SPLIT_JOBS = 8;
+struct SplitJobs {
+  SplitJob j[MAX_SPLIT_JOBS];
+  int blk0[MAX_SPLIT_JOBS + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256) split_multi_kernel(const __grid_constant__ SplitJobs g) {
+  __shared__ float tile[BK][129];
+  int i = 0;
+#pragma unroll
+  for (int q = 1; q < MAX_SPLIT_JOBS; ++q)
+    if (q < g.n && (int)blockIdx.x >= g.blk0[q]) i = q;
+  const SplitJob& j = g.j[i];
+  const int lb = (int)blockIdx.x - g.blk0[i], nb = g.blk0[i + 1] - g.blk0[i];
+  if (j.transposed == 2) {
+    const int ntiles = j.nrt * j.nkt;
+    for (int t = lb; t < ntiles; t += nb) {   // (block-uniform trip count)
+      split_tile_transposed(j.img, j.src, j.ld, j.R, j.K, j.nrt, j.nkt, t, tile);
+      __syncthreads();                          // the tile is refilled in the next round
+    }
+  } else if (j.transposed == 1) {
+    split_units<true>(j, (long long)lb * blockDim.x + threadIdx.x, (long long)nb * blockDim.x);
+  } else {
+    split_units<false>(j, (long long)lb * blockDim.x + threadIdx.x, (long long)nb * blockDim.x);
+  }
+}
+
+// Split-K partial sums of up to MAX_GROUP products -> C, in a fixed order (deterministic), one launch.
+constexpr int MAX_GROUP = 4;
+struct ReduceJob {
+  float* C;
+  const float* ws;
+  const float* bias;
+  long long ldc;
+  int M, N, splits;
+  float alpha, beta;
+};
+struct ReduceJobs {
+  ReduceJob j[MAX_GROUP];
+  int blk0[MAX_GROUP + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256) splitk_reduce_multi_kernel(const __grid_constant__ ReduceJobs g) {
+  int i = 0;
+#pragma unroll
+  for (int q = 1; q < MAX_GROUP; ++q)
+    if (q < g.n && (int)blockIdx.x >= g.blk0[q]) i = q;
+  const ReduceJob& r = g.j[i];
+  const int lb = (int)blockIdx.x - g.blk0[i], nb = g.blk0[i + 1] - g.blk0[i];
+  const int n4 = r.N >> 2;
+  const long long total = (long long)r.M * n4;
+  for (long long idx = (long long)lb * blockDim.x + threadIdx.x; idx < total; idx += (long long)nb * blockDim.x) {
+    const int m = (int)(idx / n4), n = (int)(idx - (long long)m * n4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < r.splits; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(r.ws + ((size_t)z * r.M + m) * r.N + n);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float* c = r.C + (size_t)m * r.ldc + n;
+    float o[4] = {r.alpha * a.x, r.alpha * a.y, r.alpha * a.z, r.alpha * a.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (r.beta != 0.f) o[q] += r.beta * c[q];
+      if (r.bias) o[q] += r.bias[n + q];
+      c[q] = o[q];
+    }
+  }
+}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
@@ -204,32 +284,58 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t 
       : "memory");
 }
 
-// PERSISTENT: grid = min(work items, #SMs) CTAs; work item w = (m tile, n tile, K split), m fastest (the CTAs that run
-// at the same time share the B tile in L2), item w of CTA c = c + i * gridDim.x.  The accumulator is double-buffered in
-// TMEM (2 x 128 columns): the four epilogue warps drain tile i (tcgen05.ld -> alpha/beta/bias -> 64 contiguous bytes
-// per lane and load) while the producer / MMA warps are already in the main loop of tile i+1; the shared-memory ring
-// runs continuously across tiles.  a_img / b_img: tile images of op(A) [M x K] and op(B)^T [N x K].
-__global__ void __launch_bounds__(THREADS, 1)
-gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nkt, float alpha_in,
-               const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, float beta_in,
-               const float* __restrict__ bias_in, int kt_per_split, int splits, float* __restrict__ split_ws,
-               float* __restrict__ Cout2, long long ldc_out2, int N2) {
-  // Cout2 != nullptr: TWO products that share op(A) in one launch -- C = A * B1 and C2 = A * B2 -- with the n tiles of
-  // B2's image following those of B1 in b_img (the two weight-gradient GEMMs that both contract DGIFO^T).
+// One product of a group: C[M x N] = alpha * op(A) * op(B) + beta * C (+ bias); work items [item0, item0 + ntm * ntn *
+// splits) of the launch, item = (m tile, n tile, K split) with m fastest.
+struct HlProblem {
+  float* C;
+  const float* bias;
+  const uint8_t* a_img;   // tile images of op(A) [M x K] and op(B)^T [N x K]
+  const uint8_t* b_img;
+  float* split_ws;        // splits > 1: raw partial sums [splits][M x N]; splitk_reduce applies alpha / beta / bias
+  long long ldc;
+  int M, N, nkt, ntm, ntn, splits, kt_per_split, item0;
+  float alpha, beta;
+};
+struct HlGroup {
+  HlProblem p[MAX_GROUP];
+  int n, nitems;
+};
+struct HlItem {
+  int pi, mt, nt, z;
+};
+__device__ __forceinline__ HlItem decode_item(const HlGroup& g, int w) {
+  HlItem it;
+  it.pi = 0;
+#pragma unroll
+  for (int q = 1; q < MAX_GROUP; ++q)
+    if (q < g.n && w >= g.p[q].item0) it.pi = q;
+  const HlProblem& P = g.p[it.pi];
+  const int l = w - P.item0;
+  it.mt = l % P.ntm;
+  it.nt = (l / P.ntm) % P.ntn;
+  it.z = l / (P.ntm * P.ntn);
+  return it;
+}
+
+// PERSISTENT: grid = min(work items, #SMs) CTAs over the work items of UP TO FOUR independent products (the GEMMs that
+// follow a layer's backward time loop run as one launch); within a product m is fastest (the CTAs that run at the same
+// time share the B tile in L2), item w of CTA c = c + i * gridDim.x.  The accumulator is double-buffered in TMEM
+// (2 x 128 columns): the eight epilogue warps drain tile i (tcgen05.ld -> alpha/beta/bias -> 64 contiguous bytes
+// per 4 lanes) while the producer / MMA warps are already in the main loop of tile i+1; the shared-memory ring
+// runs continuously across tiles and products.
+__global__ void __launch_bounds__(THREADS, 1) gemm_hl_kernel(const __grid_constant__ HlGroup g) {
   extern __shared__ __align__(128) uint8_t smem_raw_hl[];
   uint8_t* tiles = smem_raw_hl + ((1024u - (smem_u32(smem_raw_hl) & 1023u)) & 1023u);
   float* patches = reinterpret_cast<float*>(tiles + NSTAGE * STAGE);
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTAGE * STAGE + NEPI * PATCH);
   uint64_t* empty = full + NSTAGE;
   uint64_t* acc_full = empty + NSTAGE;   // [2] accumulator buffer complete (MMA warp -> epilogue)
-  uint64_t* acc_empty = acc_full + 2;    // [2] accumulator buffer drained (4 epilogue warps -> MMA warp)
+  uint64_t* acc_empty = acc_full + 2;    // [2] accumulator buffer drained (NEPI epilogue warps -> MMA warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int ntn1 = (N + BN - 1) / BN;
-  const int ntm = (M + BM - 1) / BM, ntn = ntn1 + (Cout2 ? (N2 + BN - 1) / BN : 0);
-  const int nitems = ntm * ntn * splits;
+  const int nitems = g.nitems;
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
@@ -258,10 +364,11 @@ gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nk
     if (lane == 0) {
       uint32_t kbc = 0;  // K blocks issued so far (ring position, continuous across work items)
       for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
-        const int mt = w % ntm, nt = (w / ntm) % ntn, z = w / (ntm * ntn);
-        const int kt0 = z * kt_per_split, nk = min(kt_per_split, nkt - kt0);
-        const uint8_t* ap = a_img + ((size_t)mt * nkt + kt0) * 2 * TILE;   // A_hi | A_lo of (mt, kt) are adjacent
-        const uint8_t* bp = b_img + ((size_t)nt * nkt + kt0) * 2 * TILE;
+        const HlItem wi = decode_item(g, w);
+        const HlProblem& P = g.p[wi.pi];
+        const int nkt = P.nkt, kt0 = wi.z * P.kt_per_split, nk = min(P.kt_per_split, nkt - kt0);
+        const uint8_t* ap = P.a_img + ((size_t)wi.mt * nkt + kt0) * 2 * TILE;   // A_hi | A_lo of (mt, kt) are adjacent
+        const uint8_t* bp = P.b_img + ((size_t)wi.nt * nkt + kt0) * 2 * TILE;
         for (int kb = 0; kb < nk; ++kb, ++kbc) {
           const uint32_t s = kbc % NSTAGE, u = kbc / NSTAGE;
           if (u > 0) mbar_wait(&empty[s], (u - 1) & 1);
@@ -278,8 +385,9 @@ gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nk
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     uint32_t kbc = 0, it = 0;
     for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
-      const int z = w / (ntm * ntn);
-      const int kt0 = z * kt_per_split, nk = min(kt_per_split, nkt - kt0);
+      const HlItem wi = decode_item(g, w);
+      const HlProblem& P = g.p[wi.pi];
+      const int kt0 = wi.z * P.kt_per_split, nk = min(P.kt_per_split, P.nkt - kt0);
       const uint32_t buf = it & 1, ub = it >> 1;
       if (ub > 0) {  // the epilogue has drained this accumulator buffer (its previous tile)
         mbar_wait(&acc_empty[buf], (ub - 1) & 1);
@@ -313,19 +421,18 @@ gemm_hl_kernel(float* __restrict__ Cout, long long ldc_out, int M, int N, int nk
   } else {
     // ------------------------------ epilogue (warps 2-9: TMEM lane quadrants 2, 3, 0, 1, 2, 3, 0, 1) -----
     const int quad = warp & 3;
-    const int N_first = N;
     uint32_t it = 0;
     for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
-      const int mt = w % ntm, nt = (w / ntm) % ntn, z = w / (ntm * ntn);
-      const bool second = nt >= ntn1;            // (dual launch) this n tile belongs to the second product
-      const int m0 = mt * BM, n0 = (second ? nt - ntn1 : nt) * BN;
-      const int N = second ? N2 : N_first;
-      float* Cm = second ? Cout2 : Cout;
-      long long ldc = second ? ldc_out2 : ldc_out;
-      float alpha = alpha_in, beta = beta_in;
-      const float* bias = second ? nullptr : bias_in;
-      if (split_ws) {  // split-K: raw partial sums to split_ws[z][M x N]; splitk_reduce applies alpha / beta / bias
-        Cm = split_ws + (size_t)z * M * N;
+      const HlItem wi = decode_item(g, w);
+      const HlProblem& P = g.p[wi.pi];
+      const int M = P.M, N = P.N;
+      const int m0 = wi.mt * BM, n0 = wi.nt * BN;
+      float* Cm = P.C;
+      long long ldc = P.ldc;
+      float alpha = P.alpha, beta = P.beta;
+      const float* bias = P.bias;
+      if (P.splits > 1) {  // split-K: raw partial sums to split_ws[z][M x N]; the reduce applies alpha / beta / bias
+        Cm = P.split_ws + (size_t)wi.z * M * N;
         ldc = N;
         alpha = 1.f;
         beta = 0.f;
@@ -419,10 +526,7 @@ cudaError_t gemm_hl_split(uint8_t* img, const float* src, long long ld, int rows
   return cudaGetLastError();
 }
 
-cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alpha, const uint8_t* a_img,
-                        const uint8_t* b_img, float beta, const float* bias, cudaStream_t stream, float* ws,
-                        size_t ws_floats, int* nlaunch, float* C2 = nullptr, long long ldc2 = 0, int N2 = 0) {
-  *nlaunch = 1;
+static cudaError_t gemm_hl_prepare(int* nsm) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -432,34 +536,58 @@ cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alph
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
-  const int nkt = (K + hl::BK - 1) / hl::BK;
-  const int ntm = (M + hl::BM - 1) / hl::BM,
-            ntn = (N + hl::BN - 1) / hl::BN + (C2 ? (N2 + hl::BN - 1) / hl::BN : 0);
-  const int tiles = ntm * ntn;
+  *nsm = 148;
+  return cudaDeviceGetAttribute(nsm, cudaDevAttrMultiProcessorCount, dev);
+}
+
+static hl::HlProblem make_problem(float* C, long long ldc, int M, int N, int K, float alpha, const uint8_t* a_img,
+                                  const uint8_t* b_img, float beta, const float* bias, int splits, float* split_ws) {
+  hl::HlProblem P;
+  P.C = C; P.bias = bias; P.a_img = a_img; P.b_img = b_img; P.ldc = ldc;
+  P.M = M; P.N = N; P.alpha = alpha; P.beta = beta;
+  P.nkt = (K + hl::BK - 1) / hl::BK;
+  P.ntm = (M + hl::BM - 1) / hl::BM;
+  P.ntn = (N + hl::BN - 1) / hl::BN;
+  P.kt_per_split = P.nkt;
+  P.splits = 1;
+  if (splits > 1) {
+    P.kt_per_split = (P.nkt + splits - 1) / splits;
+    P.splits = (P.nkt + P.kt_per_split - 1) / P.kt_per_split;
+  }
+  P.split_ws = P.splits > 1 ? split_ws : nullptr;
+  P.item0 = 0;
+  return P;
+}
+
+cudaError_t gemm_hl_run(float* C, long long ldc, int M, int N, int K, float alpha, const uint8_t* a_img,
+                        const uint8_t* b_img, float beta, const float* bias, cudaStream_t stream, float* ws,
+                        size_t ws_floats, int* nlaunch) {
+  *nlaunch = 1;
   int nsm = 148;
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = gemm_hl_prepare(&nsm);
+  if (e != cudaSuccess) return e;
+  const int nkt = (K + hl::BK - 1) / hl::BK;
+  const int tiles = ((M + hl::BM - 1) / hl::BM) * ((N + hl::BN - 1) / hl::BN);
   int splits = 1;
-  // split-K when the output tiles alone cannot fill the SMs (in_diff: 40 tiles, G(w_r_m): 28 tiles); never for a dual launch
-  if (!C2 && ws && tiles < 100 && nkt >= 4 && (N & 3) == 0) {
+  // split-K when the output tiles alone cannot fill the SMs (in_diff: 40 tiles, G(w_r_m): 28 tiles)
+  if (ws && tiles < 100 && nkt >= 4 && (N & 3) == 0) {
     splits = nsm / tiles;
     if (splits > 8) splits = 8;
     if (splits > nkt / 2) splits = nkt / 2;
     while (splits > 1 && (size_t)splits * M * N > ws_floats) --splits;
   }
-  int kts = nkt;
-  if (splits > 1) {
-    kts = (nkt + splits - 1) / splits;
-    splits = (nkt + kts - 1) / kts;
-  }
-  const int items = tiles * splits;
-  dim3 grid(items < nsm ? items : nsm), block(hl::THREADS);
-  hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(C, ldc, M, N, nkt, alpha, a_img, b_img, beta, bias, kts, splits,
-                                                        splits > 1 ? ws : nullptr, C2, ldc2, N2);
+  hl::HlGroup g;
+  memset(&g, 0, sizeof(g));
+  g.p[0] = make_problem(C, ldc, M, N, K, alpha, a_img, b_img, beta, bias, splits, ws);
+  g.n = 1;
+  g.nitems = g.p[0].ntm * g.p[0].ntn * g.p[0].splits;
+  dim3 grid(g.nitems < nsm ? g.nitems : nsm), block(hl::THREADS);
+  hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(g);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (splits > 1) {
+  if (g.p[0].splits > 1) {
     *nlaunch = 2;
-    return launch_splitk_reduce(C, ldc, M, N, alpha, beta, bias, ws, splits, stream);
+    return launch_splitk_reduce(C, ldc, M, N, alpha, beta, bias, ws, g.p[0].splits, stream);
   }
   return cudaSuccess;
 }
@@ -532,57 +660,201 @@ cudaError_t launch_gemm_hl(HlWorkspace* w, float* C, long long ldc, int M, int N
   return e;
 }
 
-// C1[M x N1] = op(A) * B1 and C2[M x N2] = op(A) * B2 in ONE launch (alpha = 1, beta = 0, no bias): op(A) is split
-// once, B1 and B2 (both stored [K x N], n contiguous) are split into consecutive n tiles of one image.  The two
-// weight-gradient GEMMs of a layer that contract DGIFO^T: G(w_gifo_x) = DGIFO^T * in, G(w_gifo_r) = DGIFO^T * R.
-cudaError_t launch_gemm_hl_dual(HlWorkspace* w, int M, int K, const float* A, long long lda, int tA, float* C1,
-                                long long ldc1, int N1, const float* B1, long long ldb1, float* C2, long long ldc2, int N2,
-                                const float* B2, long long ldb2, cudaStream_t stream, bool* handled, int* nlaunch) {
+// ---- a GROUP of products in three launches: every operand split (one launch), every product (one persistent launch),
+// every split-K reduce (one launch).  The GEMMs that follow a layer's backward time loop -- in_diff, G(w_gifo_x),
+// G(w_gifo_r), G(w_r_m) -- are independent of each other; as separate calls they were 9-10 launches of 4-20 us.
+namespace {
+// K blocks on the most loaded CTA when the items of the products (in the given order) are dealt round-robin to
+// `nsm` CTAs, for the given split counts.
+int group_makespan(const hl::HlProblem* P, int n, int nsm, std::vector<int>& load) {
+  load.assign((size_t)nsm, 0);
+  int w = 0;
+  for (int i = 0; i < n; ++i)
+    for (int z = 0; z < P[i].splits; ++z) {
+      const int len = std::min(P[i].kt_per_split, P[i].nkt - z * P[i].kt_per_split) + 1;   // (+1: per-item overhead)
+      for (int t = 0; t < P[i].ntm * P[i].ntn; ++t, ++w) load[(size_t)(w % nsm)] += len;
+    }
+  return *std::max_element(load.begin(), load.end());
+}
+}  // namespace
+
+cudaError_t launch_gemm_hl_group(HlWorkspace* w, const HlGemmDesc* d, int n, cudaStream_t stream, bool* handled,
+                                 float* ws, size_t ws_floats, int* nlaunch) {
   *handled = false;
   *nlaunch = 0;
-  if (!w || M <= 0 || N1 <= 0 || N2 <= 0 || K <= 0) return cudaSuccess;
+  if (!w || n < 1 || n > hl::MAX_GROUP) return cudaSuccess;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!al16(C1) || !al16(C2) || !al16(A) || !al16(B1) || !al16(B2)) return cudaSuccess;
-  const size_t na = gemm_hl_image_bytes(M, K), nb1 = gemm_hl_image_bytes(N1, K), nb2 = gemm_hl_image_bytes(N2, K);
-  auto grow = [&](uint8_t** p, size_t* cap, size_t need) -> cudaError_t {
-    if (need <= *cap) return cudaSuccess;
-    if (*p) {
-      cudaError_t e = cudaFree(*p);
-      if (e != cudaSuccess) return e;
-      *p = nullptr;
-      *cap = 0;
-    }
-    cudaError_t e = cudaMalloc((void**)p, need);
-    if (e == cudaSuccess) *cap = need;
-    return e;
+  for (int i = 0; i < n; ++i) {
+    if (d[i].M <= 0 || d[i].N <= 0 || d[i].K <= 0) return cudaSuccess;
+    if (!al16(d[i].C) || !al16(d[i].A) || !al16(d[i].B) || (d[i].bias && !al16(d[i].bias))) return cudaSuccess;
+  }
+  int nsm = 148;
+  cudaError_t e = gemm_hl_prepare(&nsm);
+  if (e != cudaSuccess) return e;
+
+  // ---- operands (an operand used by two products -- DGIFO^T -- is split once)
+  struct Operand {
+    const float* src;
+    long long ld;
+    int R, K;
+    bool transposed;
+    size_t off;
   };
-  cudaError_t e;
-  int b1 = 0, b2 = 0;
-  bool t1 = false, t2 = false;
-  make_job(nullptr, B1, ldb1, N1, K, true, &b1, &t1);
-  make_job(nullptr, B2, ldb2, N2, K, true, &b2, &t2);
-  if (t1 || t2) return cudaSuccess;  // operands large enough for the tiled transposed split: two ordinary GEMMs
-  if ((e = grow(&w->a, &w->a_cap, na)) != cudaSuccess) return e;
-  if ((e = grow(&w->b, &w->b_cap, nb1 + nb2)) != cudaSuccess) return e;
-  if ((e = gemm_hl_split(w->a, A, lda, M, K, tA != 0, stream)) != cudaSuccess) return e;
-  w->a_bytes = na;
-  const hl::SplitJob j1 = make_job(w->b, B1, ldb1, N1, K, true, &b1, &t1);
-  const hl::SplitJob j2 = make_job(w->b + nb1, B2, ldb2, N2, K, true, &b2, &t2);
-  hl::split_pair_kernel<<<b1 + b2, 256, 0, stream>>>(j1, j2, b1);   // (direct kernel for both: these operands are small)
+  Operand ops[2 * hl::MAX_GROUP];
+  int nops = 0, a_of[hl::MAX_GROUP], b_of[hl::MAX_GROUP];
+  size_t bytes = 0;
+  auto operand = [&](const float* src, long long ld, int R, int K, bool tr) {
+    for (int i = 0; i < nops; ++i)
+      if (ops[i].src == src && ops[i].ld == ld && ops[i].R == R && ops[i].K == K && ops[i].transposed == tr) return i;
+    ops[nops] = Operand{src, ld, R, K, tr, bytes};
+    bytes += gemm_hl_image_bytes(R, K);
+    return nops++;
+  };
+  for (int i = 0; i < n; ++i) {
+    a_of[i] = operand(d[i].A, d[i].lda, d[i].M, d[i].K, d[i].tA != 0);
+    b_of[i] = operand(d[i].B, d[i].ldb, d[i].N, d[i].K, d[i].tB == 0);
+  }
+  if (bytes > w->g_cap) {
+    if (w->g) {
+      if ((e = cudaFree(w->g)) != cudaSuccess) return e;   // (waits for the device)
+      w->g = nullptr;
+      w->g_cap = 0;
+    }
+    if ((e = cudaMalloc((void**)&w->g, bytes)) != cudaSuccess) return e;
+    w->g_cap = bytes;
+  }
+  static const int tiled_min = [] {
+    const char* v = getenv("LSTMP_B200_SPLIT_TILED_MIN");
+    return (v && *v) ? atoi(v) : 2 * 148;
+  }();
+  hl::SplitJobs sj;
+  memset(&sj, 0, sizeof(sj));
+  sj.n = nops;
+  int nblk = 0;
+  for (int i = 0; i < nops; ++i) {
+    int blocks = 0;
+    bool tiled = false;
+    sj.j[i] = make_job(w->g + ops[i].off, ops[i].src, ops[i].ld, ops[i].R, ops[i].K, ops[i].transposed, &blocks, &tiled);
+    if (ops[i].transposed && sj.j[i].nrt * sj.j[i].nkt >= tiled_min) {
+      sj.j[i].transposed = 2;
+      blocks = std::min(sj.j[i].nrt * sj.j[i].nkt, 148 * 8);
+    }
+    sj.blk0[i] = nblk;
+    nblk += blocks;
+  }
+  for (int i = nops; i <= hl::MAX_SPLIT_JOBS; ++i) sj.blk0[i] = nblk;
+  hl::split_multi_kernel<<<nblk, 256, 0, stream>>>(sj);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  int nl = 0;
-  e = gemm_hl_run(C1, ldc1, M, N1, K, 1.f, w->a, w->b, 0.f, nullptr, stream, nullptr, 0, &nl, C2, ldc2, N2);
-  *nlaunch = 2 + nl;
+  ++*nlaunch;
+
+  // ---- split-K plan: cached per shape (a few thousand simulated schedules the first time)
+  int key[1 + 3 * hl::MAX_GROUP] = {0};
+  key[0] = n;
+  for (int i = 0; i < n; ++i) {
+    key[1 + 3 * i] = d[i].M;
+    key[2 + 3 * i] = d[i].N;
+    key[3 + 3 * i] = d[i].K;
+  }
+  HlWorkspace::GroupPlan* plan = nullptr;
+  for (auto& pl : w->plans)
+    if (memcmp(pl.key, key, sizeof(key)) == 0) plan = &pl;
+  if (!plan) {
+    HlWorkspace::GroupPlan np;
+    memcpy(np.key, key, sizeof(key));
+    hl::HlProblem P[hl::MAX_GROUP];
+    int smax[hl::MAX_GROUP], cur[hl::MAX_GROUP], best[hl::MAX_GROUP];
+    for (int i = 0; i < n; ++i) {
+      const int nkt = (d[i].K + hl::BK - 1) / hl::BK;
+      smax[i] = (ws && (d[i].N & 3) == 0) ? std::max(1, std::min(6, nkt / 2)) : 1;
+      cur[i] = best[i] = 1;
+    }
+    double best_cost = 1e30;
+    std::vector<int> load;
+    for (;;) {
+      size_t wsf = 0;
+      double traffic = 0;
+      for (int i = 0; i < n; ++i) {
+        P[i] = make_problem(nullptr, 0, d[i].M, d[i].N, d[i].K, 1.f, nullptr, nullptr, 0.f, nullptr, cur[i], nullptr);
+        if (P[i].splits > 1) {
+          wsf += (size_t)P[i].splits * d[i].M * d[i].N;
+          traffic += (double)(P[i].splits + 1) * d[i].M * d[i].N * 4.0;
+        }
+      }
+      if (wsf <= ws_floats) {
+        // longest items first
+        hl::HlProblem S[hl::MAX_GROUP];
+        for (int i = 0; i < n; ++i) S[i] = P[i];
+        std::stable_sort(S, S + n, [](const hl::HlProblem& x, const hl::HlProblem& y) { return x.kt_per_split > y.kt_per_split; });
+        // 0.4 us per K block (64 KB from L2 per block), 3 us for the extra launch, the reduce at 3 TB/s
+        const double cost = 0.4 * group_makespan(S, n, nsm, load) + (traffic > 0 ? 3.0 + traffic / 3.0e6 : 0.0);
+        if (cost < best_cost) {
+          best_cost = cost;
+          for (int i = 0; i < n; ++i) best[i] = cur[i];
+        }
+      }
+      int i = 0;
+      while (i < n && ++cur[i] > smax[i]) cur[i++] = 1;
+      if (i == n) break;
+    }
+    for (int i = 0; i < n; ++i) np.splits[i] = best[i];
+    w->plans.push_back(np);
+    plan = &w->plans.back();
+  }
+
+  // ---- the products, longest items first
+  int order[hl::MAX_GROUP];
+  hl::HlProblem P[hl::MAX_GROUP];
+  size_t ws_off = 0;
+  for (int i = 0; i < n; ++i) {
+    order[i] = i;
+    P[i] = make_problem(d[i].C, d[i].ldc, d[i].M, d[i].N, d[i].K, d[i].alpha, w->g + ops[a_of[i]].off,
+                        w->g + ops[b_of[i]].off, d[i].beta, d[i].bias, plan->splits[i], ws ? ws + ws_off : nullptr);
+    if (P[i].splits > 1) ws_off += (size_t)P[i].splits * d[i].M * d[i].N;
+  }
+  std::stable_sort(order, order + n, [&](int x, int y) { return P[x].kt_per_split > P[y].kt_per_split; });
+  hl::HlGroup g;
+  memset(&g, 0, sizeof(g));
+  g.n = n;
+  hl::ReduceJobs rj;
+  memset(&rj, 0, sizeof(rj));
+  int rblk = 0;
+  for (int k = 0; k < n; ++k) {
+    const int i = order[k];
+    g.p[k] = P[i];
+    g.p[k].item0 = g.nitems;
+    g.nitems += P[i].ntm * P[i].ntn * P[i].splits;
+    if (P[i].splits > 1) {
+      hl::ReduceJob& r = rj.j[rj.n];
+      r.C = d[i].C; r.ws = P[i].split_ws; r.bias = d[i].bias; r.ldc = d[i].ldc;
+      r.M = d[i].M; r.N = d[i].N; r.splits = P[i].splits; r.alpha = d[i].alpha; r.beta = d[i].beta;
+      int rb = (int)(((long long)d[i].M * (d[i].N >> 2) + 255) / 256);
+      rb = std::max(1, std::min(rb, 148 * 4));
+      rj.blk0[rj.n++] = rblk;
+      rblk += rb;
+    }
+  }
+  for (int i = rj.n; i <= hl::MAX_GROUP; ++i) rj.blk0[i] = rblk;
+  dim3 grid(g.nitems < nsm ? g.nitems : nsm), block(hl::THREADS);
+  hl::gemm_hl_kernel<<<grid, block, hl::SMEM, stream>>>(g);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  ++*nlaunch;
+  if (rj.n > 0) {
+    hl::splitk_reduce_multi_kernel<<<rblk, 256, 0, stream>>>(rj);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ++*nlaunch;
+  }
   *handled = true;
-  return e;
+  return cudaSuccess;
 }
 
 void gemm_hl_free(HlWorkspace* w) {
   if (!w) return;
   if (w->a) cudaFree(w->a);
   if (w->b) cudaFree(w->b);
-  w->a = w->b = nullptr;
-  w->a_cap = w->b_cap = w->a_bytes = 0;
+  if (w->g) cudaFree(w->g);
+  w->a = w->b = w->g = nullptr;
+  w->a_cap = w->b_cap = w->a_bytes = w->g_cap = 0;
+  w->plans.clear();
 }
 
 }  // namespace lstmp

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include <vector>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -135,13 +137,35 @@ cudaError_t launch_gemm(float* C, long long ldc, int M, int N, int K, float alph
 struct HlWorkspace {
   uint8_t *a = nullptr, *b = nullptr;   // tile images of op(A) [M x K] and op(B)^T [N x K]
   size_t a_cap = 0, b_cap = 0, a_bytes = 0;
+  uint8_t* g = nullptr;                 // image arena of a group launch
+  size_t g_cap = 0;
+  struct GroupPlan {                    // split-K counts chosen for a group of shapes (key = n, then M, N, K of each)
+    int key[13];
+    int splits[4];
+  };
+  std::vector<GroupPlan> plans;
 };
 cudaError_t launch_gemm_hl(HlWorkspace* w, float* C, long long ldc, int M, int N, int K, float alpha, const float* A,
                            long long lda, int tA, const float* B, long long ldb, int tB, float beta, const float* bias,
                            cudaStream_t stream, bool* handled, float* ws, size_t ws_floats, int* nlaunch, bool reuse_a);
-cudaError_t launch_gemm_hl_dual(HlWorkspace* w, int M, int K, const float* A, long long lda, int tA, float* C1,
-                                long long ldc1, int N1, const float* B1, long long ldb1, float* C2, long long ldc2, int N2,
-                                const float* B2, long long ldb2, cudaStream_t stream, bool* handled, int* nlaunch);
+// Up to four independent products C_i = alpha_i * op(A_i) * op(B_i) + beta_i * C_i (+ bias_i) in three launches (all
+// operand splits, all products, all split-K reduces).  tA / tB as in launch_gemm.
+struct HlGemmDesc {
+  float* C;
+  long long ldc;
+  int M, N, K;
+  float alpha;
+  const float* A;
+  long long lda;
+  int tA;
+  const float* B;
+  long long ldb;
+  int tB;
+  float beta;
+  const float* bias;
+};
+cudaError_t launch_gemm_hl_group(HlWorkspace* w, const HlGemmDesc* d, int n, cudaStream_t stream, bool* handled,
+                                 float* ws, size_t ws_floats, int* nlaunch);
 void gemm_hl_free(HlWorkspace* w);
 
 // corr = G + momentum*corr ; param -= lr*corr   over the flat arena

@@ -14,7 +14,7 @@ ABI_SYMBOLS = [
     "lstmp_b200_get_flat", "lstmp_b200_set_flat", "lstmp_b200_arena", "lstmp_b200_get_state",
     "lstmp_b200_set_state", "lstmp_b200_reset", "lstmp_b200_propagate", "lstmp_b200_backpropagate",
     "lstmp_b200_update", "lstmp_b200_allreduce_grads_nccl", "lstmp_b200_get_info", "lstmp_b200_get_record",
-    "lstmp_b200_timing_enable", "lstmp_b200_timing_read", "lstmp_b200_debug_gemm",
+    "lstmp_b200_timing_enable", "lstmp_b200_timing_read", "lstmp_b200_debug_gemm", "lstmp_b200_debug_gemm_group",
     "lstmp_b200_xent_create", "lstmp_b200_xent_destroy", "lstmp_b200_xent_eval_masked",
     "lstmp_b200_xent_get_stats", "lstmp_b200_xent_reset_stats",
     "lstmp_b200_update_clipped", "lstmp_b200_time_shift", "lstmp_b200_set_nccl",
@@ -295,6 +295,32 @@ def debug_gemm(backend, C, M, N, K, alpha, A, tA, B, tB, beta=0.0, bias=None):
                                  ctypes.c_void_p(A.data_ptr()), A.stride(0), int(tA), ctypes.c_void_p(B.data_ptr()),
                                  B.stride(0), int(tB), float(beta),
                                  ctypes.c_void_p(bias.data_ptr()) if bias is not None else None, st))
+
+
+class GemmDesc(ctypes.Structure):
+    """lstmp_b200_gemm_desc (include/lstmp_b200.h)."""
+    _fields_ = [("C", ctypes.c_void_p), ("ldc", ctypes.c_size_t), ("M", ctypes.c_int), ("N", ctypes.c_int),
+                ("K", ctypes.c_int), ("alpha", ctypes.c_float), ("A", ctypes.c_void_p), ("lda", ctypes.c_size_t),
+                ("tA", ctypes.c_int), ("B", ctypes.c_void_p), ("ldb", ctypes.c_size_t), ("tB", ctypes.c_int),
+                ("beta", ctypes.c_float), ("bias", ctypes.c_void_p)]
+
+
+def debug_gemm_group(problems):
+    """problems: list of (C, M, N, K, alpha, A, tA, B, tB, beta, bias) as for debug_gemm; one grouped launch
+    (lstmp_b200_debug_gemm_group).  Returns the number of kernel launches."""
+    import torch
+    L = load_library()
+    L.lstmp_b200_debug_gemm_group.argtypes = [ctypes.c_int, ctypes.POINTER(GemmDesc), ctypes.c_void_p]
+    L.lstmp_b200_debug_gemm_group.restype = ctypes.c_int
+    arr = (GemmDesc * len(problems))()
+    for d, (C, M, N, K, alpha, A, tA, B, tB, beta, bias) in zip(arr, problems):
+        d.C, d.ldc, d.M, d.N, d.K, d.alpha = C.data_ptr(), C.stride(0), M, N, K, float(alpha)
+        d.A, d.lda, d.tA, d.B, d.ldb, d.tB = A.data_ptr(), A.stride(0), int(tA), B.data_ptr(), B.stride(0), int(tB)
+        d.beta, d.bias = float(beta), (bias.data_ptr() if bias is not None else None)
+    rc = L.lstmp_b200_debug_gemm_group(len(problems), arr, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc < 0:
+        _chk(rc)
+    return rc
 
 
 def time_shift(x, out, shift):

@@ -84,3 +84,55 @@ def test_gemm_hl_pitched_and_alpha_beta(eng):
     assert _case(eng, 2, 3200, 512, 1280, 1, 0, pad=8) <= 2e-5
     assert _case(eng, 2, 1280, 3200, 512, 0, 1, alpha=1.0, beta=0.0, bias=False) <= 2e-5
     assert _case(eng, 2, 256, 384, 200, 0, 0, alpha=-1.5, beta=1.0, bias=False, seed=3) <= 2e-5
+
+
+# ---- grouped launch: the four products after a layer's backward loop as one split + one GEMM + one reduce launch ----
+def _group_case(eng, shapes, seed=0, shared_a=()):
+    """shapes: list of (M, N, K, tA, tB, alpha, beta, bias); shared_a: pairs (i, j) -- product j reuses product i's A."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    probs, refs = [], []
+    for idx, (M, N, K, tA, tB, alpha, beta, bias) in enumerate(shapes):
+        A = torch.randn((K, M) if tA else (M, K), device="cuda", generator=g)
+        for (i, j) in shared_a:
+            if j == idx:
+                A = probs[i][5]
+        B = torch.randn((N, K) if tB else (K, N), device="cuda", generator=g)
+        C = torch.randn((M, N), device="cuda", generator=g)
+        bvec = torch.randn(N, device="cuda", generator=g) if bias else None
+        ref = alpha * ((A.t() if tA else A).double() @ (B.t() if tB else B).double()) + beta * C.double()
+        if bias:
+            ref = ref + bvec.double()
+        probs.append((C, M, N, K, alpha, A, tA, B, tB, beta, bvec))
+        refs.append(ref)
+    nl = eng.debug_gemm_group(probs)
+    torch.cuda.synchronize()
+    errs = [((p[0].double() - r).abs().max() / r.abs().max()).item() for p, r in zip(probs, refs)]
+    return nl, errs
+
+
+def test_gemm_group_backward_layer2(eng):
+    # cfg3 layer 2: in_diff, G(w_gifo_x), G(w_gifo_r) (both on DGIFO^T), G(w_r_m)
+    shapes = [(1280, 512, 3200, 0, 0, 1.0, 0.0, False), (3200, 512, 1280, 1, 0, 1.0, 0.0, False),
+              (3200, 512, 1280, 1, 0, 1.0, 0.0, False), (512, 800, 1280, 1, 0, 1.0, 0.0, False)]
+    for rep in range(2):   # second call: cached plan, reused image arena
+        nl, errs = _group_case(eng, shapes, seed=rep, shared_a=((1, 2),))
+        assert 2 <= nl <= 3
+        assert max(errs) <= 2e-5, errs
+
+
+def test_gemm_group_backward_layer1(eng):
+    shapes = [(3200, 40, 1280, 1, 0, 1.0, 0.0, False), (3200, 512, 1280, 1, 0, 1.0, 0.0, False),
+              (512, 800, 1280, 1, 0, 1.0, 0.0, False)]
+    nl, errs = _group_case(eng, shapes, shared_a=((0, 1),))
+    assert max(errs) <= 2e-5, errs
+
+
+def test_gemm_group_mixed_small_and_ragged(eng):
+    # alpha / beta / bias per product, ragged tiles, N not a multiple of 4 (no split-K for that product), tiny products
+    shapes = [(132, 260, 36, 1, 1, 0.7, 0.3, True), (4, 8, 4, 0, 1, 1.0, 0.0, False),
+              (80, 3200, 40, 0, 1, 0.5, 1.0, True), (200, 50, 1000, 0, 0, 1.0, 0.5, False)]
+    nl, errs = _group_case(eng, shapes)
+    assert max(errs) <= 2e-5, errs
+    nl, errs = _group_case(eng, [(640, 512, 16624, 0, 0, 1.0, 0.0, False)])   # a group of one, deep K (split-K)
+    assert max(errs) <= 2e-5, errs
