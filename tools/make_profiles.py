@@ -3,8 +3,7 @@
 
   ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_rN.csv \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
-  ncu --set full --clock-control none --import-source on -k regex:"lstmp_.*_kernel|gemm_hl_kernel|split_hl" -s 20 -c 24 \
-      -o gpurun_out/prof_rN python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
+  tools/gpu_call_ncu_full.sh   (ncu --set full --clock-control none --import-source on, two whole steps = 26 launches)
 
 usage: tools/make_profiles.py <round> [launches.csv] [prof.ncu-rep]
 writes profiles/rN_launches.csv, rN_launch_summary.md, rN_ncu_set_full_selected.csv, rN_ncu_digest.md, traffic.json
@@ -126,15 +125,28 @@ def ncu_summary(rnd, rep):
 
     stalls = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
     out = ["# Round %s ncu --set full digest (tools/make_profiles.py; source: gpurun_out/prof_r%s.ncu-rep, command in"
-           % (rnd, rnd), "# tools/make_profiles.py's header; per-launch values of the FIRST captured launch of each kernel)", ""]
+           % (rnd, rnd), "# tools/make_profiles.py's header; per-launch values of the FIRST captured launch of each kernel / grid)", ""]
+    # one step of the workload, launch by launch (the capture covers two whole steps: the first half)
+    out += ["## All captured launches of one step (cfg3: layer 1 forward, layer 2 forward, layer 2 backward + its GEMM group, "
+            "layer 1 backward + its GEMM group)", "",
+            "| # | kernel | grid | duration us | tensor pipe % | DRAM read + write MB | L2 hit % |", "|---|---|---|---|---|---|---|"]
+    for i, r in enumerate(data[:(len(data) + 1) // 2]):
+        g = lambda m: val(r, m)
+        out.append("| %d | `%s` | %d | %.1f | %.1f | %.1f | %.0f |" % (
+            i, r[col["Kernel Name"]].split("(")[0], g("launch__grid_size"), g("gpu__time_duration.sum"),
+            g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") or 0.0,
+            (g("dram__bytes_read.sum") or 0.0) + (g("dram__bytes_write.sum") or 0.0), g("lts__t_sector_hit_rate.pct") or 0.0))
+    out.append("")
     seen = set()
     for r in data:
         name = r[col["Kernel Name"]].split("(")[0]
-        if name in seen:
+        # the same kernel on another problem (input GEMM vs a layer's GEMM group) is told apart by grid and DRAM bytes
+        key = (name, r[col["launch__grid_size"]], int(val(r, "dram__bytes_read.sum") or 0))
+        if key in seen:
             continue
-        seen.add(name)
+        seen.add(key)
         g = lambda m: val(r, m)
-        out.append("## `%s`" % name)
+        out.append("## `%s` (grid %s, launch #%d of the table)" % (name, r[col["launch__grid_size"]], data.index(r)))
         out.append("")
         out.append("| metric | value |")
         out.append("|---|---|")
