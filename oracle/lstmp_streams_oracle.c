@@ -23,11 +23,17 @@
  *                  which live in upstream Kaldi and are NOT in the reference tree;
  *                  restated below as the overflow-safe forms Kaldi uses.
  *
- * PARITY UNPINNED: the reference ships no tests, fixtures or golden vectors for
- * this path and cannot be compiled here (Kaldi's base/util/nnet-component/cblas
- * are not vendored).  This oracle is pinned instead against (a) an independent
- * torch-autograd restatement of the equations and (b) fp64 finite differences
- * (tests/test_oracle.py, tests/golden/make_golden.py).
+ * PARITY PINNED against the reference's own source: the reference ships no tests,
+ * fixtures or golden vectors for this path, so oracle/_ref (`make -C oracle ref`)
+ * compiles the UNMODIFIED bd-nnet-lstm-projected-streams.h, nnet-lstm-projected.h,
+ * nnet-time-shift.h and nnet-loss.cc where they lie under /root/reference, together
+ * with the kaldi-matrix.cc / cu-matrix.cc method bodies on the path, against a
+ * CPU-computing Kaldi surface (oracle/ref_build/), and tests/test_ref_pin.py checks
+ * this restatement against it: bit-for-bit with the same SGEMM, <= 1e-6 otherwise
+ * (cfg2, cfg3 both layers, S=1/T=100, reset + carry, clamp saturation, momentum
+ * 0 / 0.9).  tests/golden/*.npz were generated from oracle/_ref
+ * (tests/golden/make_golden.py).  Independent cross-checks: a torch-autograd
+ * restatement of the equations and fp64 finite differences (tests/test_oracle.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.  The product (kaldi-lstm_b200/) never does.

@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's masked cross-entropy
 (`Xent::EvalMasked`, google/nnet/nnet-loss.cc:76-164), dense-matrix formulation exactly as the reference
-computes it on its CPU matrix path.  Parity UNPINNED by the reference (it ships no tests for this function);
-pinned here against an independent torch formulation in tests/test_xent_oracle.py.
+computes it on its CPU matrix path.  The reference ships no tests for this function; parity is PINNED against the
+reference's own nnet-loss.cc compiled into oracle/_ref (tests/test_ref_pin.py::test_xent_eval_masked_matches_reference,
+hard and soft targets, out-of-range pdf) and against an independent torch formulation (tests/test_xent_oracle.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline legs may import this module; the product
 (kaldi-lstm_b200/) never does.

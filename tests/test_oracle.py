@@ -1,9 +1,11 @@
 """Pins the C oracle (oracle/lstmp_streams_oracle.c).
 
-The reference ships no golden vectors for this path ("parity
-unpinned"), so the oracle is pinned against (a) an independent torch-autograd restatement
-of the equations, (b) fp64 central finite differences, and (c) its own committed golden
-fixtures (tests/golden/), so a silent change of the oracle is caught.
+The reference ships no golden vectors for this path, so the
+primary pin is tests/test_ref_pin.py: the oracle against oracle/_ref, the reference's own
+headers compiled here.  This file adds the checks that do not depend on the reference's
+control flow being right: (a) an independent torch-autograd restatement of the equations,
+(b) fp64 central finite differences, and (c) the committed golden fixtures (tests/golden/,
+generated from oracle/_ref), so a silent change of the oracle is caught.
 """
 import os
 
