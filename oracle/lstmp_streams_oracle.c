@@ -31,7 +31,7 @@
  * CPU-computing Kaldi surface (oracle/ref_build/), and tests/test_ref_pin.py checks
  * this restatement against it: bit-for-bit with the same SGEMM, <= 1e-6 otherwise
  * (cfg2, cfg3 both layers, S=1/T=100, reset + carry, clamp saturation, momentum
- * 0 / 0.9).  tests/golden/*.npz were generated from oracle/_ref
+ * 0 / 0.9).  The .npz fixtures under tests/golden/ were generated from oracle/_ref
  * (tests/golden/make_golden.py).  Independent cross-checks: a torch-autograd
  * restatement of the equations and fp64 finite differences (tests/test_oracle.py).
  *
