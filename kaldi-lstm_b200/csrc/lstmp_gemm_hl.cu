@@ -12,9 +12,12 @@
 //      [128 rows x 64 k] tile the ready-made SWIZZLE_128B K-major shared-memory image of its hi half and of its lo
 //      half (16 KB each), zero-padded to whole tiles; an operand stored with the contraction index as the ROW index
 //      (m/n-contiguous, e.g. DGIFO^T for the weight gradients) is transposed on the way.
-//   2. gemm_hl_kernel: one thread issues four 16 KB cp.async.bulk copies per 64-deep K block straight into the UMMA
-//      ring (mbarrier expect_tx), one warp issues 16 MMAs per block, four warps run the epilogue.  No loader warps, no
-//      register pass, no generic-proxy stores into operand tiles, no bounds logic on the operand side.
+//   2. gemm_hl_kernel (persistent, 320 threads): one thread issues two 32 KB cp.async.bulk copies per 64-deep K block
+//      (A_hi | A_lo, B_hi | B_lo) straight into the UMMA ring (mbarrier expect_tx), one warp issues 16 MMAs per block
+//      into one of two TMEM accumulators, eight warps drain the other one.  No loader warps, no register pass, no
+//      generic-proxy stores into operand tiles, no bounds logic on the operand side.
+//   3. launch_gemm_hl_group: up to four independent products -- the contractions after a layer's backward time loop --
+//      as ONE split launch (split_multi_kernel), ONE persistent product launch and ONE split-K reduce launch.
 //
 // (lstmp_gemm_tc.cu moves 32 KB in, 32 KB back out and 64 KB of hi/lo tiles through shared memory per 32-deep K block
 // with eight loader warps and reaches ~1.9 k cycles per block against 0.78 k of MMA time)
