@@ -1,4 +1,5 @@
-"""Kaldi nnet1 TEXT model files for the components on the recipe's path, and the google <-> standard conversion.
+"""Kaldi nnet1 model files (text AND binary) for the components on the recipe's path, and the google <-> standard
+conversion.
 
 Host-only (no GPU): SURVEY.md section 8(f) rank 4.  The reference describes the conversion as manual text editing
 (README.md:19-29 and Q3): `nnet-copy --binary=false`, change `<Transmit>` to `<TimeShift> ... <Shift> k` (k = the
@@ -10,7 +11,15 @@ standard/nnet/nnet-lstm-projected.h:139-152), so the conversion never touches th
 Text layout (upstream nnet-nnet.cc / nnet-component.cc, kaldi-matrix.cc:1172-1211): `<Nnet>`, then per component
 `<Type> output_dim input_dim` followed by the component's own data, then `</Nnet>`.  Matrices are ` [` rows `]`,
 vectors ` [ a b c ]`; reading is whitespace-tokenised and the shapes come from the component header.
+
+Binary layout (what `nnet-initialize` / the trainer write by default; upstream io-funcs + kaldi-matrix.cc:1172-1211, token
+order of the LSTM from LPS.h:101-150): the file starts with `\0B`; tokens are `<Token>` + one space in both modes; an
+int32 / float is one size byte (4) + 4 little-endian bytes; a float matrix is `FM ` + int32 rows + int32 cols + the
+rows back to back, a float vector `FV ` + int32 dim + data.  `parse_nnet_binary` / `format_nnet_binary` are pinned against
+the reference's own ReadData / WriteData (oracle/_ref, tests/test_ref_pin.py).
 """
+import struct
+
 import numpy as np
 
 LSTM_TYPES = ("<LstmProjectedStreams>", "<LstmProjected>")
@@ -111,6 +120,190 @@ def parse_nnet(text):
     return comps
 
 
+# ---- binary ------------------------------------------------------------------------------------------------------
+BINARY_HEADER = b"\0B"
+_FLOAT_ATTRS = ("<LearnRateCoef>", "<BiasLearnRateCoef>", "<MaxNorm>")
+
+
+class _BinReader:
+    """Kaldi's binary-mode readers (upstream base/io-funcs-inl.h): ReadToken, ReadBasicType, Matrix / Vector Read."""
+
+    def __init__(self, data):
+        self.d = bytes(data)
+        self.i = 0
+
+    def _skip_ws(self):
+        while self.i < len(self.d) and self.d[self.i:self.i + 1].isspace():
+            self.i += 1
+
+    def peek_token(self):
+        save = self.i
+        try:
+            return self.token()
+        except RuntimeError:
+            return None
+        finally:
+            self.i = save
+
+    def token(self):
+        self._skip_ws()                                    # operator>>(string) skips leading white space
+        j = self.i
+        while j < len(self.d) and not self.d[j:j + 1].isspace():
+            j += 1
+        if j == self.i:
+            raise RuntimeError("ReadToken failed: unexpected end of binary nnet")
+        if j >= len(self.d):
+            raise RuntimeError("ReadToken: expected space after token")
+        tok = self.d[self.i:j].decode("ascii", "replace")
+        self.i = j + 1                                     # exactly one space is consumed: raw bytes may follow
+        return tok
+
+    def expect(self, tok):
+        got = self.token()
+        if got != tok:
+            raise RuntimeError("Expected token %s, got %s" % (tok, got))
+
+    def basic(self, fmt):
+        if self.i >= len(self.d) or self.d[self.i] != 4:
+            raise RuntimeError("ReadBasicType: size byte %r where 4 was expected" % self.d[self.i:self.i + 1])
+        if self.i + 5 > len(self.d):
+            raise RuntimeError("ReadBasicType failed: truncated file")
+        v = struct.unpack_from("<" + fmt, self.d, self.i + 1)[0]
+        self.i += 5
+        return v
+
+    def int32(self):
+        return self.basic("i")
+
+    def float32(self):
+        return self.basic("f")
+
+    def _data(self, n):
+        nb = 4 * n
+        if n < 0 or self.i + nb > len(self.d):
+            raise RuntimeError("matrix/vector data runs past the end of the file")
+        a = np.frombuffer(self.d, dtype="<f4", count=n, offset=self.i).astype(np.float32)
+        self.i += nb
+        return a
+
+    def matrix(self, shape=None):
+        tok = self.token()
+        if tok != "FM":
+            raise RuntimeError("Expected token FM, got %s (only float matrices are supported)" % tok)
+        r, c = self.int32(), self.int32()
+        if shape is not None and (r, c) != tuple(shape):
+            raise RuntimeError("matrix is %d x %d, the component header implies %s" % (r, c, (shape,)))
+        return self._data(r * c).reshape(r, c)
+
+    def vector(self, shape=None):
+        tok = self.token()
+        if tok != "FV":
+            raise RuntimeError("Expected token FV, got %s (only float vectors are supported)" % tok)
+        n = self.int32()
+        if shape is not None and (n,) != tuple(shape):
+            raise RuntimeError("vector has %d elements, the component header implies %s" % (n, (shape,)))
+        return self._data(n)
+
+    def array(self, shape):
+        return self.matrix(shape) if len(shape) == 2 else self.vector(shape)
+
+
+def _read_component_data(c, rd):
+    """ReadData of one component from a _BinReader (same grammar as the text branch of parse_nnet)."""
+    typ, out_dim, in_dim = c.type, c.output_dim, c.input_dim
+    if typ in ("<Transmit>", "<Softmax>"):
+        pass
+    elif typ == "<TimeShift>":
+        rd.expect("<Shift>")
+        c.attrs.append(("<Shift>", rd.int32()))
+    elif typ in LSTM_TYPES:
+        rd.expect("<CellDim>")
+        ncell = rd.int32()
+        c.attrs.append(("<CellDim>", ncell))
+        if typ == "<LstmProjectedStreams>":
+            rd.expect("<NumStream>")
+            c.attrs.append(("<NumStream>", rd.int32()))
+        for _, shape in lstm_shapes(out_dim, in_dim, ncell):
+            c.arrays.append(rd.array(shape))
+    elif typ == "<AffineTransform>":
+        while rd.peek_token() in _FLOAT_ATTRS:
+            k = rd.token()
+            c.attrs.append((k, float(rd.float32())))
+        c.arrays.append(rd.matrix((out_dim, in_dim)))
+        c.arrays.append(rd.vector((out_dim,)))
+    else:
+        raise RuntimeError("Unknown component type %s" % typ)
+
+
+def parse_nnet_binary(data):
+    """Kaldi nnet1 BINARY model (with or without the leading `\\0B`) -> list of NnetComponent."""
+    data = bytes(data)
+    if data[:2] == BINARY_HEADER:
+        data = data[2:]
+    rd = _BinReader(data)
+    rd.expect("<Nnet>")
+    comps = []
+    while True:
+        typ = rd.token()
+        if typ == "</Nnet>":
+            break
+        if typ == "<!EndOfComponent>":        # written by later Kaldi versions after every component
+            continue
+        c = NnetComponent(typ, rd.int32(), rd.int32())
+        _read_component_data(c, rd)
+        comps.append(c)
+    return comps
+
+
+def _tok(t):
+    return t.encode("ascii") + b" "
+
+
+def _i32(v):
+    return b"\x04" + struct.pack("<i", int(v))
+
+
+def _f32(v):
+    return b"\x04" + struct.pack("<f", float(v))
+
+
+def _array_binary(a):
+    a = np.ascontiguousarray(a, dtype="<f4")
+    if a.ndim == 1:
+        return _tok("FV") + _i32(a.shape[0]) + a.tobytes()
+    return _tok("FM") + _i32(a.shape[0]) + _i32(a.shape[1]) + a.tobytes()
+
+
+def component_data_binary(c):
+    """What the component's WriteData(os, binary=true) emits (LPS.h:133-150 for the LSTM)."""
+    out = []
+    for k, v in c.attrs:
+        out.append(_tok(k) + (_f32(v) if k in _FLOAT_ATTRS else _i32(v)))
+    out.extend(_array_binary(a) for a in c.arrays)
+    return b"".join(out)
+
+
+def format_nnet_binary(comps, header=True):
+    out = [BINARY_HEADER if header else b"", _tok("<Nnet>")]
+    for c in comps:
+        out.append(_tok(c.type) + _i32(c.output_dim) + _i32(c.input_dim) + component_data_binary(c))
+    out.append(_tok("</Nnet>"))
+    return b"".join(out)
+
+
+def read_nnet(path):
+    """Model file in either mode (Kaldi's Input::Open test: binary files start with `\\0B`)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    return parse_nnet_binary(data) if data[:2] == BINARY_HEADER else parse_nnet(data.decode("ascii"))
+
+
+def write_nnet(path, comps, binary=True):
+    with open(path, "wb") as f:
+        f.write(format_nnet_binary(comps) if binary else format_nnet(comps).encode("ascii"))
+
+
+# ---- text ----------------------------------------------------------------------------------------------------------
 def _fmt(v):
     return repr(float(np.float32(v))) if isinstance(v, (float, np.floating)) else str(v)
 

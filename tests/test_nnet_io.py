@@ -115,3 +115,54 @@ def test_component_model_file_roundtrip(monkeypatch):
     with pytest.raises(RuntimeError):
         klb.LstmProjectedStreams.FromNnetComponent(comps[0])
 
+
+
+# ---- binary files ------------------------------------------------------------------------------------------------
+def test_binary_roundtrip_and_text_equivalence(tmp_path):
+    comps, flat = _google_model()
+    data = nio.format_nnet_binary(comps)
+    assert data[:2] == b"\0B" and data[2:9] == b"<Nnet> " and data.endswith(b"</Nnet> ")
+    # header of the LSTM component: marker, then output_dim and input_dim as size byte 4 + little-endian int32
+    k = data.index(b"<LstmProjectedStreams> ") + len(b"<LstmProjectedStreams> ")
+    assert data[k:k + 10] == b"\x04\x03\x00\x00\x00\x04\x06\x00\x00\x00"
+    assert data[k + 10:k + 20] == b"<CellDim> " and data[k + 20:k + 25] == b"\x04\x04\x00\x00\x00"
+    back = nio.parse_nnet_binary(data)
+    assert [c.type for c in back] == ["<Transmit>", "<LstmProjectedStreams>", "<AffineTransform>", "<Softmax>"]
+    np.testing.assert_array_equal(nio.lstm_flat_params(back[1]), flat)
+    assert back[2].attrs == comps[2].attrs and back[1].attrs == comps[1].attrs
+    assert nio.format_nnet_binary(back) == data
+    assert nio.format_nnet(back) == nio.format_nnet(comps)                  # same model in text
+    # files: the mode is detected from the first two bytes, as Kaldi's Input does
+    pb, pt = tmp_path / "final.nnet", tmp_path / "final.nnet.txt"
+    nio.write_nnet(str(pb), comps, binary=True)
+    nio.write_nnet(str(pt), comps, binary=False)
+    for p in (pb, pt):
+        rd = nio.read_nnet(str(p))
+        np.testing.assert_array_equal(nio.lstm_flat_params(rd[1]), flat)
+        np.testing.assert_array_equal(rd[2].arrays[0], comps[2].arrays[0])
+    # google -> standard on a binary model (README.md:19-29 does it on text after nnet-copy --binary=false)
+    std = nio.google_to_standard(nio.read_nnet(str(pb)), shift=5)
+    again = nio.parse_nnet_binary(nio.format_nnet_binary(std))
+    assert [c.type for c in again] == ["<TimeShift>", "<LstmProjected>", "<AffineTransform>", "<Softmax>"]
+    assert again[0].attr("<Shift>") == 5 and again[1].attr("<NumStream>") is None
+
+
+def test_binary_reader_tolerates_end_of_component_and_rejects_garbage():
+    comps, flat = _google_model()
+    data = nio.format_nnet_binary(comps, header=False)
+    # later Kaldi versions close every component with <!EndOfComponent>
+    marked = data.replace(b"<Softmax> ", b"<!EndOfComponent> <Softmax> ")
+    assert [c.type for c in nio.parse_nnet_binary(marked)] == [c.type for c in comps]
+    with pytest.raises(RuntimeError, match="Expected token <Nnet>"):
+        nio.parse_nnet_binary(b"\0B<Nnot> ")
+    with pytest.raises(RuntimeError, match="past the end|truncated|ReadToken"):
+        nio.parse_nnet_binary(data[:len(data) // 2])
+    bad = data.replace(b"FM ", b"DM ", 1)                                    # a double matrix: not what nnet1 writes
+    with pytest.raises(RuntimeError, match="Expected token FM"):
+        nio.parse_nnet_binary(bad)
+    k = data.index(b"<CellDim> ") + len(b"<CellDim> ")
+    wrong = data[:k] + b"\x04\x05\x00\x00\x00" + data[k + 5:]              # CellDim 5: shapes no longer match
+    with pytest.raises(RuntimeError, match="component header implies"):
+        nio.parse_nnet_binary(wrong)
+    with pytest.raises(RuntimeError, match="size byte"):
+        nio.parse_nnet_binary(data[:k] + b"\x08" + data[k + 1:])

@@ -173,6 +173,32 @@ def test_reference_write_read_roundtrip_matches_nnet_io():
     assert np.array_equal(r2.get_params(), flat)
 
 
+def test_binary_model_io_matches_the_reference_bytes():
+    """nnet_io's BINARY writer emits byte for byte what the reference's WriteData(os, binary=true) emits (LPS.h:133-150
+    token order; FM / FV containers of kaldi-matrix.cc:1172-1211), its reader parses the reference's bytes, and the
+    reference's ReadData (LPS.h:101-131) accepts what nnet_io writes."""
+    import kaldi_lstm_b200 as klb
+    nio = klb.nnet_io
+    I, C, R, S = 5, 6, 4, 3
+    flat, _, r = _pair(I, C, R, S, 0.3, 44)
+    ref_bytes = r.write(binary=True)
+    comp = nio.lstm_component_from_flat(flat, R, I, C, num_stream=S)
+    assert nio.component_data_binary(comp) == ref_bytes
+    # the reference's bytes inside a whole binary <Nnet> (header, component marker + dims as upstream Component::Write)
+    body = b"\0B<Nnet> <LstmProjectedStreams> " + b"\x04" + np.int32(R).tobytes() + b"\x04" + np.int32(I).tobytes() + \
+        ref_bytes + b"</Nnet> "
+    comps = nio.parse_nnet_binary(body)
+    assert len(comps) == 1 and comps[0].type == "<LstmProjectedStreams>"
+    assert comps[0].attr("<CellDim>") == C and comps[0].attr("<NumStream>") == S
+    assert np.array_equal(nio.lstm_flat_params(comps[0]), flat)
+    assert nio.format_nnet_binary(comps) == body
+    # and back into the reference
+    flat2 = oracle_py.init_params(I, C, R, 0.2, 45)
+    r2 = ref_py.RefLstm(I, C, R, S)
+    r2.read(nio.component_data_binary(nio.lstm_component_from_flat(flat2, R, I, C, num_stream=S)), binary=True)
+    assert np.array_equal(r2.get_params(), flat2)
+
+
 def test_standard_lstm_projected_is_the_s1_case_with_grad_clip():
     """standard/nnet/nnet-lstm-projected.h == streams component at S = 1 from zero state, plus the element-wise
     gradient clip at 50 in Update (:480-493) = oracle.clip_grads."""
