@@ -16,7 +16,7 @@ Binary layout (what `nnet-initialize` / the trainer write by default; upstream i
 order of the LSTM from LPS.h:101-150): the file starts with `\0B`; tokens are `<Token>` + one space in both modes; an
 int32 / float is one size byte (4) + 4 little-endian bytes; a float matrix is `FM ` + int32 rows + int32 cols + the
 rows back to back, a float vector `FV ` + int32 dim + data.  `parse_nnet_binary` / `format_nnet_binary` are pinned against
-the reference's own ReadData / WriteData (oracle/_ref, tests/test_ref_pin.py).
+the reference's own ReadData / WriteData compiled here (tests/test_ref_pin.py).
 """
 import struct
 
