@@ -23,6 +23,7 @@ import struct
 import numpy as np
 
 LSTM_TYPES = ("<LstmProjectedStreams>", "<LstmProjected>")
+TRANSFORM_TYPES = ("<AddShift>", "<Rescale>")   # the feature transform in front of the network (CMVN)
 
 
 class NnetComponent:
@@ -113,6 +114,11 @@ def parse_nnet(text):
                 k = tk.next()
                 c.attrs.append((k, float(tk.next())))
             c.arrays.append(tk.array((out_dim, in_dim)))
+            c.arrays.append(tk.array((out_dim,)))
+        elif typ in TRANSFORM_TYPES:                                  # google/feature_transform.nnet.txt:2-5
+            if tk.peek() == "<LearnRateCoef>":                        # (later Kaldi versions; absent in the reference's file)
+                k = tk.next()
+                c.attrs.append((k, float(tk.next())))
             c.arrays.append(tk.array((out_dim,)))
         else:
             raise RuntimeError("Unknown component type %s" % typ)
@@ -230,6 +236,11 @@ def _read_component_data(c, rd):
             k = rd.token()
             c.attrs.append((k, float(rd.float32())))
         c.arrays.append(rd.matrix((out_dim, in_dim)))
+        c.arrays.append(rd.vector((out_dim,)))
+    elif typ in TRANSFORM_TYPES:
+        if rd.peek_token() == "<LearnRateCoef>":
+            k = rd.token()
+            c.attrs.append((k, float(rd.float32())))
         c.arrays.append(rd.vector((out_dim,)))
     else:
         raise RuntimeError("Unknown component type %s" % typ)
@@ -356,6 +367,28 @@ def standard_to_google(comps, num_stream):
         else:
             out.append(c)
     return out
+
+
+def feature_transform(comps):
+    """(shift, scale) of a feature-transform nnet = `<AddShift>` then `<Rescale>` (google/feature_transform.nnet.txt:2-5),
+    the two vectors the device-side stream dispatch fuses into its gather kernel: feat = (x + shift) * scale.  Either
+    component may be absent (None); anything else -- another component type, the opposite order, a dimension change --
+    is not a transform the dispatcher can fuse and raises."""
+    shift = scale = None
+    for c in comps:
+        if c.type not in TRANSFORM_TYPES or c.input_dim != c.output_dim:
+            raise RuntimeError("feature transform: cannot fuse component %s %d %d" % (c.type, c.output_dim, c.input_dim))
+        if c.type == "<AddShift>":
+            if shift is not None or scale is not None:
+                raise RuntimeError("feature transform: expected at most one <AddShift>, before <Rescale>")
+            shift = np.asarray(c.arrays[0], np.float32)
+        else:
+            if scale is not None:
+                raise RuntimeError("feature transform: expected at most one <Rescale>")
+            scale = np.asarray(c.arrays[0], np.float32)
+    if shift is not None and scale is not None and shift.shape != scale.shape:
+        raise RuntimeError("feature transform: <AddShift> and <Rescale> dimensions differ")
+    return shift, scale
 
 
 def targets_delay(comps):

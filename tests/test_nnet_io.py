@@ -166,3 +166,58 @@ def test_binary_reader_tolerates_end_of_component_and_rejects_garbage():
         nio.parse_nnet_binary(wrong)
     with pytest.raises(RuntimeError, match="size byte"):
         nio.parse_nnet_binary(data[:k] + b"\x08" + data[k + 1:])
+
+
+# ---- the feature transform in front of the network (google/feature_transform.nnet.txt) ------------------------------
+def _transform_text(shift, scale, coef=False):
+    def vec(v):
+        return " [ " + " ".join("%.6f" % x for x in v) + " ]\n"
+    lr = "<LearnRateCoef> 0 " if coef else ""
+    d = len(shift)
+    return "<Nnet> \n<AddShift> %d %d %s\n%s<Rescale> %d %d %s\n%s</Nnet> \n" % (d, d, lr, vec(shift), d, d, lr, vec(scale))
+
+
+@pytest.mark.parametrize("coef", [False, True])
+def test_feature_transform_is_parsed_into_the_dispatchers_two_vectors(coef):
+    rng = np.random.RandomState(3)
+    shift = (-17 + rng.randn(40)).astype(np.float32)
+    scale = (0.25 + 0.01 * rng.rand(40)).astype(np.float32)
+    comps = nio.parse_nnet(_transform_text(shift, scale, coef))
+    assert [c.type for c in comps] == ["<AddShift>", "<Rescale>"]
+    sh, sc = nio.feature_transform(comps)
+    np.testing.assert_allclose(sh, shift, atol=1e-6)
+    np.testing.assert_allclose(sc, scale, atol=1e-6)
+    # binary round trip of the same two components
+    back = nio.parse_nnet_binary(nio.format_nnet_binary(comps))
+    sh2, sc2 = nio.feature_transform(back)
+    np.testing.assert_array_equal(sh2, sh)
+    np.testing.assert_array_equal(sc2, sc)
+    # what DeviceStreamDispatcher(shift=sh, scale=sc) fuses into its gather kernel: (x + shift) * scale, i.e. raw
+    # log-mel features ~ N(17, 3.6^2) come out normalised
+    x = (rng.randn(1000, 40) * 3.6 + 17).astype(np.float32)
+    y = (x + sh) * sc
+    assert y.dtype == np.float32 and abs(y.mean()) < 0.5 and 0.5 < y.std() < 1.5
+
+
+def test_feature_transform_rejects_what_it_cannot_fuse():
+    d = 4
+    a = nio.NnetComponent("<AddShift>", d, d, [], [np.zeros(d, np.float32)])
+    r = nio.NnetComponent("<Rescale>", d, d, [], [np.ones(d, np.float32)])
+    assert nio.feature_transform([]) == (None, None)
+    assert nio.feature_transform([r])[0] is None and nio.feature_transform([a])[1] is None
+    for bad in ([r, a], [a, a], [a, r, r], [nio.NnetComponent("<Softmax>", d, d)],
+                [a, nio.NnetComponent("<Rescale>", 5, 5, [], [np.ones(5, np.float32)])]):
+        with pytest.raises(RuntimeError, match="feature transform"):
+            nio.feature_transform(bad)
+
+
+def test_the_references_own_transform_file():
+    """The file the reference ships (read where it lies; absent on the GPU box)."""
+    import os
+    path = "/root/reference/google/feature_transform.nnet.txt"
+    if not os.path.exists(path):
+        pytest.skip("reference tree absent")
+    comps = nio.read_nnet(path)
+    sh, sc = nio.feature_transform(comps)
+    assert sh.shape == sc.shape == (40,)
+    assert -20 < sh.min() and sh.max() < -15 and 0.2 < sc.min() and sc.max() < 0.35   # SURVEY 8d: shift -17..-16, scale 0.25..0.30
