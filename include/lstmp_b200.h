@@ -175,8 +175,8 @@ int lstmp_b200_get_record(lstmp_b200_handle_t h, int backward, float* dst, size_
 /* Test hook: run one of the engine's GEMM kernels on caller device buffers.
  *   C[M x N] = alpha * op(A) * op(B) + beta * C (+ bias[n]);  tA/tB: 0 = as stored, 1 = transposed
  *   (op(A) is M x K, op(B) is K x N; row-major with leading dimensions, as CuMatrixBase::AddMatMat,
- *   cu-matrix.cc:909-945).  backend: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (returns
- *   LSTMP_B200_EUNSUPPORTED if the shape/alignment is not handled by that kernel). */
+ *   cu-matrix.cc:909-945).  backend: 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 on bf16 hi/lo tile images (the
+ *   engine's default; returns LSTMP_B200_EUNSUPPORTED if the shape/alignment is not handled by that kernel). */
 int lstmp_b200_debug_gemm(int backend, float* C, size_t ldc, int M, int N, int K, float alpha, const float* A,
                           size_t lda, int tA, const float* B, size_t ldb, int tB, float beta, const float* bias,
                           void* stream);
