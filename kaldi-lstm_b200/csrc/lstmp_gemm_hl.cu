@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "lstmp_common.cuh"
+#include "lstmp_gemm_plan.h"
 #include "lstmp_kernels.h"
 #include "lstmp_tc.cuh"
 
@@ -231,6 +232,8 @@ __global__ void __launch_bounds__(256) split_multi_kernel(const __grid_constant_
 
 // Split-K partial sums of up to MAX_GROUP products -> C, in a fixed order (deterministic), one launch.
 constexpr int MAX_GROUP = 4;
+static_assert(BM == hlplan::kBM && BN == hlplan::kBN && BK == hlplan::kBK && MAX_GROUP == hlplan::kMaxGroup,
+              "lstmp_gemm_plan.h plans for this kernel's tile");
 struct ReduceJob {
   float* C;
   const float* ws;
@@ -548,15 +551,12 @@ static hl::HlProblem make_problem(float* C, long long ldc, int M, int N, int K, 
   hl::HlProblem P;
   P.C = C; P.bias = bias; P.a_img = a_img; P.b_img = b_img; P.ldc = ldc;
   P.M = M; P.N = N; P.alpha = alpha; P.beta = beta;
-  P.nkt = (K + hl::BK - 1) / hl::BK;
-  P.ntm = (M + hl::BM - 1) / hl::BM;
-  P.ntn = (N + hl::BN - 1) / hl::BN;
-  P.kt_per_split = P.nkt;
-  P.splits = 1;
-  if (splits > 1) {
-    P.kt_per_split = (P.nkt + splits - 1) / splits;
-    P.splits = (P.nkt + P.kt_per_split - 1) / P.kt_per_split;
-  }
+  const hlplan::Tiling t = hlplan::tiling(M, N, K, splits);
+  P.nkt = t.nkt;
+  P.ntm = t.ntm;
+  P.ntn = t.ntn;
+  P.kt_per_split = t.kt_per_split;
+  P.splits = t.splits;
   P.split_ws = P.splits > 1 ? split_ws : nullptr;
   P.item0 = 0;
   return P;
@@ -666,21 +666,6 @@ cudaError_t launch_gemm_hl(HlWorkspace* w, float* C, long long ldc, int M, int N
 // ---- a GROUP of products in three launches: every operand split (one launch), every product (one persistent launch),
 // every split-K reduce (one launch).  The GEMMs that follow a layer's backward time loop -- in_diff, G(w_gifo_x),
 // G(w_gifo_r), G(w_r_m) -- are independent of each other; as separate calls they were 9-10 launches of 4-20 us.
-namespace {
-// K blocks on the most loaded CTA when the items of the products (in the given order) are dealt round-robin to
-// `nsm` CTAs, for the given split counts.
-int group_makespan(const hl::HlProblem* P, int n, int nsm, std::vector<int>& load) {
-  load.assign((size_t)nsm, 0);
-  int w = 0;
-  for (int i = 0; i < n; ++i)
-    for (int z = 0; z < P[i].splits; ++z) {
-      const int len = std::min(P[i].kt_per_split, P[i].nkt - z * P[i].kt_per_split) + 1;   // (+1: per-item overhead)
-      for (int t = 0; t < P[i].ntm * P[i].ntn; ++t, ++w) load[(size_t)(w % nsm)] += len;
-    }
-  return *std::max_element(load.begin(), load.end());
-}
-}  // namespace
-
 cudaError_t launch_gemm_hl_group(HlWorkspace* w, const HlGemmDesc* d, int n, cudaStream_t stream, bool* handled,
                                  float* ws, size_t ws_floats, int* nlaunch) {
   *handled = false;
@@ -764,42 +749,9 @@ cudaError_t launch_gemm_hl_group(HlWorkspace* w, const HlGemmDesc* d, int n, cud
   if (!plan) {
     HlWorkspace::GroupPlan np;
     memcpy(np.key, key, sizeof(key));
-    hl::HlProblem P[hl::MAX_GROUP];
-    int smax[hl::MAX_GROUP], cur[hl::MAX_GROUP], best[hl::MAX_GROUP];
-    for (int i = 0; i < n; ++i) {
-      const int nkt = (d[i].K + hl::BK - 1) / hl::BK;
-      smax[i] = (ws && (d[i].N & 3) == 0) ? std::max(1, std::min(6, nkt / 2)) : 1;
-      cur[i] = best[i] = 1;
-    }
-    double best_cost = 1e30;
-    std::vector<int> load;
-    for (;;) {
-      size_t wsf = 0;
-      double traffic = 0;
-      for (int i = 0; i < n; ++i) {
-        P[i] = make_problem(nullptr, 0, d[i].M, d[i].N, d[i].K, 1.f, nullptr, nullptr, 0.f, nullptr, cur[i], nullptr);
-        if (P[i].splits > 1) {
-          wsf += (size_t)P[i].splits * d[i].M * d[i].N;
-          traffic += (double)(P[i].splits + 1) * d[i].M * d[i].N * 4.0;
-        }
-      }
-      if (wsf <= ws_floats) {
-        // longest items first
-        hl::HlProblem S[hl::MAX_GROUP];
-        for (int i = 0; i < n; ++i) S[i] = P[i];
-        std::stable_sort(S, S + n, [](const hl::HlProblem& x, const hl::HlProblem& y) { return x.kt_per_split > y.kt_per_split; });
-        // 0.4 us per K block (64 KB from L2 per block), 3 us for the extra launch, the reduce at 3 TB/s
-        const double cost = 0.4 * group_makespan(S, n, nsm, load) + (traffic > 0 ? 3.0 + traffic / 3.0e6 : 0.0);
-        if (cost < best_cost) {
-          best_cost = cost;
-          for (int i = 0; i < n; ++i) best[i] = cur[i];
-        }
-      }
-      int i = 0;
-      while (i < n && ++cur[i] > smax[i]) cur[i++] = 1;
-      if (i == n) break;
-    }
-    for (int i = 0; i < n; ++i) np.splits[i] = best[i];
+    hlplan::Shape shp[hl::MAX_GROUP];
+    for (int i = 0; i < n; ++i) shp[i] = hlplan::Shape{d[i].M, d[i].N, d[i].K};
+    hlplan::plan_group(shp, n, nsm, ws != nullptr, ws_floats, np.splits);
     w->plans.push_back(np);
     plan = &w->plans.back();
   }
